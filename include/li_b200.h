@@ -1,0 +1,216 @@
+/*
+ * li_b200.h -- C ABI of libli_b200.so: the B200 (sm_100a) implementation of the
+ * interpolation hot path of emmt/LinearInterpolators.jl.
+ *
+ * This is the drop-in boundary.  The reference is pure Julia and crosses no FFI
+ * today; a maintainer replaces the *bodies* of the Julia methods cited below by
+ * `ccall`s into these entry points (see INTEGRATION.md for the stubs), keeping the
+ * LazyAlgebra signatures `vcreate(P, A, x, scratch)` and
+ * `apply!(alpha, P, A, x, scratch, beta, y)` untouched.  Citations are
+ * file:line into the reference tree.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*
+ *     (NULL = the legacy default stream);
+ *   - arrays are column-major (Julia layout); `npre`/`npost` are the products of
+ *     the dimensions before/after the interpolated one (CartesianIndices(predims)
+ *     / (postdims) in src/tabulated.jl:355-357);
+ *   - every function returns an li_status; li_last_error() gives the message of
+ *     the last failure on the calling thread;
+ *   - `*_dev` pointers are device pointers, `*_host` pointers are host pointers
+ *     (pinned memory from li_host_alloc makes the copies asynchronous);
+ *   - apply entry points are asynchronous on `stream` unless stated otherwise.
+ *     There is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with LI_ERR_CUDA.
+ */
+#ifndef LI_B200_H
+#define LI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LI_B200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define LI_API __attribute__((visibility("default")))
+#else
+#define LI_API
+#endif
+
+typedef enum {
+    LI_OK = 0,
+    LI_ERR_ARG = 1,         /* ErrorException / ArgumentError / AssertionError in the reference */
+    LI_ERR_DIM = 2,         /* DimensionMismatch (src/tabulated.jl:198, src/sparse.jl:624-651) */
+    LI_ERR_INEXACT = 3,     /* InexactError of trunc(Int, f) (src/boundaries.jl:81,105,147) */
+    LI_ERR_BOUNDS = 4,      /* "out of bound index in interpolation table" (src/tabulated.jl:212) */
+    LI_ERR_UNSUPPORTED = 5, /* kernel family / size not built */
+    LI_ERR_CUDA = 6,
+    LI_ERR_NOMEM = 7
+} li_status;
+
+typedef enum { LI_F32 = 0, LI_F64 = 1 } li_dtype;
+
+/* InterpolationKernels 0.1.x kernel families (src/LinearInterpolators.jl:19-52). */
+typedef enum {
+    LI_RECTANGULAR = 0,       /* RectangularSpline,       S = 1 */
+    LI_LINEAR = 1,            /* LinearSpline,            S = 2 */
+    LI_QUADRATIC = 2,         /* QuadraticSpline,         S = 3 */
+    LI_CUBIC = 3,             /* CubicSpline (B-spline),  S = 4 */
+    LI_CATMULLROM = 4,        /* CatmullRomSpline,        S = 4 */
+    LI_CARDINALCUBIC = 5,     /* CardinalCubicSpline(c),  S = 4, params[0] = c */
+    LI_KEYS = 6,              /* KeysSpline(a),           S = 4, params[0] = a */
+    LI_MITCHELLNETRAVALI = 7, /* MitchellNetravaliSpline(b, c), S = 4, params[0..1] */
+    LI_LANCZOS = 8            /* LanczosKernel(S), S even, 2 <= S <= 16 */
+} li_family;
+
+/* Boundary tag B of Kernel{T,S,B}; selects FlatLimits / SafeFlatLimits
+ * (src/types.jl:27-52, src/boundaries.jl:37-42). */
+typedef enum { LI_FLAT = 0, LI_SAFEFLAT = 1 } li_boundary;
+
+/* Adjoint variants. */
+typedef enum {
+    LI_VARIANT_AUTO = 0,   /* deterministic gather */
+    LI_VARIANT_GATHER = 1, /* deterministic: transposed table, ascending (row, tap) order */
+    LI_VARIANT_ATOMIC = 2  /* red.global.add scatter; not run-to-run deterministic */
+} li_variant;
+
+#define LI_MAX_S 16
+
+/* Value description of a Kernel{T,S,B} (the kernel types themselves stay in Julia). */
+typedef struct {
+    int32_t family;   /* li_family */
+    int32_t S;        /* kernel size */
+    int32_t boundary; /* li_boundary */
+    int32_t dtype;    /* li_dtype: the kernel's floating-point type T */
+    double params[4];
+} li_kernel_desc;
+
+typedef struct li_table li_table; /* opaque device-resident (J, W) table */
+
+typedef struct {
+    int32_t dtype, S;
+    int64_t nrows, ncols;
+    int32_t windowed; /* every row is clamp(base + s): eligible for the staged/fused kernels */
+    int32_t monotone; /* window bases are non-decreasing */
+} li_table_info;
+
+/* ---- library / device ---------------------------------------------------- */
+LI_API int li_version(void);
+LI_API const char *li_last_error(void);
+LI_API const char *li_status_string(int status);
+LI_API int li_device_count(int *count);
+LI_API int li_set_device(int device);
+LI_API int li_get_device(int *device);
+LI_API int li_num_sms(int *count);
+
+/* ---- memory (replaces Array{T}(undef, dims) of vcreate when data lives on the
+ *      device: src/tabulated.jl:305-327, src/sparse.jl:187-199,619-630,
+ *      src/nonseparable.jl:65-75) ------------------------------------------- */
+LI_API int li_malloc(void **dev_ptr, size_t bytes);
+LI_API int li_free(void *dev_ptr);
+LI_API int li_host_alloc(void **host_ptr, size_t bytes); /* pinned */
+LI_API int li_host_free(void *host_ptr);
+LI_API int li_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+LI_API int li_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+LI_API int li_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes, void *stream);
+LI_API int li_memset_zero(void *dst_dev, size_t bytes, void *stream);
+LI_API int li_stream_sync(void *stream);
+/* vscale!(y, beta) of LazyAlgebra (call sites src/tabulated.jl:353,386,
+ * src/sparse.jl:211,255,656,699, ...): beta == 0 fills zeros without reading. */
+LI_API int li_vscale(int dtype, void *y_dev, int64_t n, double beta, void *stream);
+
+/* ---- tables --------------------------------------------------------------
+ * li_table_create: positions -> (J, W) on the device with Flat / SafeFlat
+ * clamping.  Replaces __maketables (src/tabulated.jl:137-189) and _sparsecoefs
+ * (src/sparse.jl:140-164), i.e. getcoefs (src/boundaries.jl:77-156) looped over
+ * the rows.  `pos` holds nrows positions already converted to the kernel type T
+ * (convert(T, X[i]), src/tabulated.jl:153) and may be a host or device pointer.
+ * Synchronous (it reports LI_ERR_INEXACT). */
+LI_API int li_table_create(const li_kernel_desc *ker, const void *pos, int pos_on_device, int64_t nrows,
+                    int64_t ncols, void *stream, li_table **out);
+/* li_table_import: adopt tables computed elsewhere (custom kernels evaluated in
+ * Julia).  J is Int64, 1-based, S x nrows column-major exactly like A.J
+ * (src/tabulated.jl:32) / A.J of the sparse operators (src/sparse.jl:44,522);
+ * W like A.W / A.C.  Host pointers.  Performs the bound check of __fullcheck
+ * (src/tabulated.jl:206-215) / _check (src/sparse.jl:166-185,802-817) once. */
+LI_API int li_table_import(int dtype, int S, int64_t nrows, int64_t ncols, const int64_t *J_host,
+                    const void *W_host, void *stream, li_table **out);
+/* li_table_export: materialise coefficients(A) / columns(A) (src/tabulated.jl:43-44,
+ * src/sparse.jl:67-68,527-528) on the host in the reference's layout. */
+LI_API int li_table_export(const li_table *t, int64_t *J_host, void *W_host, void *stream);
+LI_API int li_table_get_info(const li_table *t, li_table_info *info);
+LI_API int li_table_destroy(li_table *t);
+
+/* ---- table-backed operators ------------------------------------------------
+ * dst <- alpha * P(A) * src + beta * dst along one dimension.
+ * Direct  : src is [npre, ncols, npost], dst is [npre, nrows, npost]
+ *           __direct! (src/tabulated.jl:394-439), SparseInterpolator Direct
+ *           (src/sparse.jl:201-244, npre = npost = 1), _apply_direct!
+ *           (src/sparse.jl:719-774).
+ * Adjoint : src is [npre, nrows, npost], dst is [npre, ncols, npost]
+ *           __adjoint! (src/tabulated.jl:441-478), src/sparse.jl:246-275,776-800.
+ * alpha == 0 only scales dst by beta; beta == 0 never reads dst. */
+LI_API int li_tab_apply(int adjoint, const li_table *t, int64_t npre, int64_t npost, double alpha,
+                 const void *src_dev, double beta, void *dst_dev, int variant, void *stream);
+
+/* Separable N-d operator H = A_1 * A_2 * ... * A_ndim (A_k interpolates dimension
+ * k), the LazyAlgebra composition of test/benchmarks.jl:27-29,44-49.  A NULL entry
+ * in `tabs` leaves that dimension untouched (its length is dims_in[k]).
+ * Direct : src [ncols_1..ncols_n, nbatch] -> dst [nrows_1..nrows_n, nbatch];
+ * Adjoint: the reverse.  ndim = 2 uses a fused kernel (one pass over HBM) when
+ * both tables are windowed; otherwise per-dimension passes through `workspace`.
+ * `dims_other[k]` is only read for NULL tables. */
+LI_API int li_sep_workspace_bytes(int adjoint, int ndim, const li_table *const *tabs,
+                           const int64_t *dims_other, int64_t nbatch, size_t *bytes);
+LI_API int li_sep_apply(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other,
+                 int64_t nbatch, double alpha, const void *src_dev, double beta, void *dst_dev,
+                 void *workspace_dev, size_t workspace_bytes, int variant, void *stream);
+
+/* ---- operators with on-the-fly coefficients --------------------------------
+ * 1-D: apply!(alpha, P, ker, x, src, beta, dst), src/unidimensional.jl:95-245.
+ * Direct: src[len] -> dst[n]; Adjoint: src[n] -> dst[len].  x_dev: n positions of type T.
+ * Synchronous (reports LI_ERR_INEXACT). */
+LI_API int li_otf1d_apply(int adjoint, const li_kernel_desc *ker, const void *x_dev, int64_t n,
+                   int64_t len, double alpha, const void *src_dev, double beta, void *dst_dev,
+                   int variant, void *stream);
+/* 2-D separable: apply!(alpha, P, ker1, x1, ker2, x2, src, beta, dst),
+ * src/separable.jl:56-162.  Direct: src[m1,m2,nbatch] -> dst[n1,n2,nbatch].
+ * Coefficients are generated on the device per call (no table survives the call).
+ * Synchronous. */
+LI_API int li_sep2d_otf_apply(int adjoint, const li_kernel_desc *ker1, const void *x1_dev, int64_t n1,
+                       const li_kernel_desc *ker2, const void *x2_dev, int64_t n2, int64_t m1,
+                       int64_t m2, int64_t nbatch, double alpha, const void *src_dev, double beta,
+                       void *dst_dev, void *stream);
+/* 2-D affine: apply!(alpha, P, ker1, ker2, R, src, beta, dst),
+ * src/nonseparable.jl:147-264, and the Mapping methods :77-101.
+ * R = (xx, xy, x, yx, yy, y) of AffineTransform2D; rows = (n1, n2) is the output
+ * size of the direct operator, cols = (m1, m2) its input size; nbatch images are
+ * contiguous along a third dimension.  Synchronous unless flags & LI_FLAG_ASYNC. */
+#define LI_FLAG_ASYNC 1 /* skip the InexactError read-back; errors surface at the next sync call */
+LI_API int li_affine2d_apply(int adjoint, const li_kernel_desc *ker1, const li_kernel_desc *ker2,
+                      const double R[6], int64_t n1, int64_t n2, int64_t m1, int64_t m2,
+                      int64_t nbatch, double alpha, const void *src_dev, double beta,
+                      void *dst_dev, int variant, int flags, void *stream);
+
+/* ---- host-buffer front ends (Julia `Array` arguments) ----------------------
+ * Same semantics with HOST src/dst: stage through the device (H2D, kernel, D2H)
+ * on `stream` and synchronise.  Correct but PCIe-bound; still no CPU compute. */
+LI_API int li_tab_apply_host(int adjoint, const li_table *t, int64_t npre, int64_t npost, double alpha,
+                      const void *src_host, double beta, void *dst_host, int variant, void *stream);
+LI_API int li_sep_apply_host(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other,
+                      int64_t nbatch, double alpha, const void *src_host, double beta,
+                      void *dst_host, int variant, void *stream);
+
+/* ---- counters --------------------------------------------------------------
+ * Number of CUDA kernels this library has launched in this process (all entry
+ * points); bench.py reports the difference over the timed region. */
+LI_API int64_t li_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LI_B200_H */

@@ -1,0 +1,91 @@
+// li_common.cuh -- internal declarations shared by the translation units of libli_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <map>
+
+#include "li_b200.h"
+
+namespace li {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define LI_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            li::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                          __LINE__);                                                       \
+            return e__ == cudaErrorMemoryAllocation ? LI_ERR_NOMEM : LI_ERR_CUDA;          \
+        }                                                                                  \
+    } while (0)
+
+#define LI_CHECK_LAUNCH()                                                                  \
+    do {                                                                                   \
+        li::count_launch();                                                                \
+        LI_CUDA(cudaGetLastError());                                                       \
+    } while (0)
+
+#define LI_REQUIRE(cond, status, ...)                                                      \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            li::set_error(__VA_ARGS__);                                                    \
+            return (status);                                                               \
+        }                                                                                  \
+    } while (0)
+
+inline size_t dtype_size(int dtype) { return dtype == LI_F32 ? 4 : 8; }
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Tile granularities for which per-table footprint bounds are cached.
+struct AdjointIndex;
+
+}  // namespace li
+
+// Device-resident table.  J is kept as int32, 0-based; the reference layout
+// (Int64, 1-based, S x nrows) is produced by li_table_export.
+struct li_table {
+    int32_t dtype = 0, S = 0;
+    int64_t nrows = 0, ncols = 0;
+    int32_t *J = nullptr;     // [nrows*S], 0-based, clamped
+    void *W = nullptr;        // [nrows*S], T
+    int32_t *base = nullptr;  // [nrows] canonical window base (0-based tap s is clamp(base+s)); valid iff windowed
+    bool windowed = false;
+    bool monotone = false;
+    // lazily built adjoint helpers (guarded by mu)
+    mutable std::mutex mu;
+    // generic transposed (CSC) table: entries sorted by (column, row, tap)
+    mutable int32_t *colptr = nullptr;  // [ncols+1]
+    mutable int32_t *tent = nullptr;    // [nrows*S] entry id e = row*S + tap
+    // monotone windowed tables: rowstart[k] = first row whose window reaches column k  ([ncols+1])
+    mutable int32_t *rowstart = nullptr;
+    // cached footprint bounds: key = tile rows G -> max over aligned tiles of (max base - min base)
+    mutable std::map<int, int> fwd_span;
+    // cached: key = tile cols G -> max over aligned column tiles of number of contributing rows
+    mutable std::map<int, int> adj_rows;
+};
+
+namespace li {
+int table_ensure_csc(const li_table *t, cudaStream_t st);
+int table_ensure_rowstart(const li_table *t, cudaStream_t st);
+int table_fwd_span(const li_table *t, int G, cudaStream_t st, int *span);
+int table_adj_rows(const li_table *t, int G, cudaStream_t st, int *rows);
+// builds a table from device positions into preallocated device arrays (used by the OTF operators)
+int table_create_impl(const li_kernel_desc *ker, const void *pos_dev, int64_t nrows, int64_t ncols,
+                      cudaStream_t st, li_table **out);
+int tab_apply_impl(int adjoint, const li_table *t, int64_t npre, int64_t npost, double alpha,
+                   const void *src, double beta, void *dst, int variant, cudaStream_t st);
+int vscale_impl(int dtype, void *y, int64_t n, double beta, cudaStream_t st);
+int sep2d_fused_supported(const li_table *t1, const li_table *t2);
+int sep2d_fused_apply(int adjoint, const li_table *t1, const li_table *t2, int64_t nbatch,
+                      double alpha, const void *src, double beta, void *dst, cudaStream_t st,
+                      bool *done);
+}  // namespace li

@@ -1,0 +1,226 @@
+// li_sep.cu -- separable N-d operators H = A_1 * A_2 * ... * A_n and the on-the-fly
+// front ends that build their coefficients on the device per call.
+//
+// Reference: LazyAlgebra composition of per-dimension operators
+// (test/benchmarks.jl:27-29,44-49; H*x = A_1*(...*(A_n*x)), H'*y = A_n'*(...*(A_1'*y)))
+// and the on-the-fly operators src/unidimensional.jl:95-245, src/separable.jl:56-162.
+#include <vector>
+
+#include "li_common.cuh"
+
+namespace li {
+
+struct SepPlan {
+    int npass = 0;
+    int dim[3];           // dimension (0-based) of each pass, in application order
+    int64_t npre[3], npost[3];
+    int64_t out_elems[3];  // elements of the array produced by each pass
+    int64_t in_elems = 0;
+};
+
+static int make_plan(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other, int64_t nbatch,
+                     SepPlan *plan)
+{
+    LI_REQUIRE(ndim >= 1 && ndim <= 3, LI_ERR_UNSUPPORTED, "separable operators support 1 to 3 dimensions");
+    LI_REQUIRE(tabs, LI_ERR_ARG, "null table list");
+    LI_REQUIRE(nbatch >= 0, LI_ERR_DIM, "negative batch size");
+    int64_t cur[3];
+    int dtype = -1;
+    for (int k = 0; k < ndim; ++k) {
+        if (tabs[k]) {
+            cur[k] = adjoint ? tabs[k]->nrows : tabs[k]->ncols;
+            if (dtype < 0) dtype = tabs[k]->dtype;
+            LI_REQUIRE(dtype == tabs[k]->dtype, LI_ERR_ARG, "tables of a separable operator must share one floating-point type");
+        } else {
+            LI_REQUIRE(dims_other && dims_other[k] >= 0, LI_ERR_DIM, "missing length of an untouched dimension");
+            cur[k] = dims_other[k];
+        }
+    }
+    LI_REQUIRE(dtype >= 0, LI_ERR_ARG, "at least one table is required");
+    plan->in_elems = nbatch;
+    for (int k = 0; k < ndim; ++k) plan->in_elems *= cur[k];
+    plan->npass = 0;
+    // Direct applies A_n first; Adjoint applies A_1' first.
+    for (int step = 0; step < ndim; ++step) {
+        const int k = adjoint ? step : ndim - 1 - step;
+        if (!tabs[k]) continue;
+        int64_t pre = 1, post = nbatch;
+        for (int d = 0; d < k; ++d) pre *= cur[d];
+        for (int d = k + 1; d < ndim; ++d) post *= cur[d];
+        const int p = plan->npass++;
+        plan->dim[p] = k;
+        plan->npre[p] = pre;
+        plan->npost[p] = post;
+        cur[k] = adjoint ? tabs[k]->ncols : tabs[k]->nrows;
+        plan->out_elems[p] = pre * post * cur[k];
+    }
+    return LI_OK;
+}
+
+static int sep_workspace(const SepPlan &plan, int dtype, size_t *bytes, size_t *half)
+{
+    // ping-pong buffers holding every intermediate (all but the last pass's output)
+    int64_t m = 0;
+    for (int p = 0; p + 1 < plan.npass; ++p) m = std::max(m, plan.out_elems[p]);
+    const size_t one = ((size_t)m * dtype_size(dtype) + 255) & ~(size_t)255;
+    *half = one;
+    *bytes = plan.npass >= 3 ? 2 * one : (plan.npass == 2 ? one : 0);
+    return LI_OK;
+}
+
+static int sep_apply_impl(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other,
+                          int64_t nbatch, double alpha, const void *src, double beta, void *dst, void *workspace,
+                          size_t workspace_bytes, int variant, cudaStream_t st)
+{
+    SepPlan plan;
+    int rc = make_plan(adjoint, ndim, tabs, dims_other, nbatch, &plan);
+    if (rc != LI_OK) return rc;
+    int dtype = LI_F32;
+    for (int k = 0; k < ndim; ++k)
+        if (tabs[k]) dtype = tabs[k]->dtype;
+    LI_REQUIRE(dst, LI_ERR_ARG, "null destination");
+    if (plan.npass == 0 || plan.in_elems == 0) return LI_OK;
+    const int64_t nout = plan.out_elems[plan.npass - 1];
+    if (alpha == 0.0) return vscale_impl(dtype, dst, nout, beta, st);
+    LI_REQUIRE(src, LI_ERR_ARG, "null source");
+
+    // fused single-pass kernel for two windowed tables on dimensions 1 and 2
+    if (ndim == 2 && tabs[0] && tabs[1] && variant != LI_VARIANT_ATOMIC) {
+        bool done = false;
+        rc = sep2d_fused_apply(adjoint, tabs[0], tabs[1], nbatch, alpha, src, beta, dst, st, &done);
+        if (rc != LI_OK || done) return rc;
+    }
+
+    size_t need = 0, half = 0;
+    sep_workspace(plan, dtype, &need, &half);
+    LI_REQUIRE(workspace_bytes >= need && (need == 0 || workspace), LI_ERR_ARG,
+               "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    const void *in = src;
+    for (int p = 0; p < plan.npass; ++p) {
+        const bool last = p == plan.npass - 1;
+        void *out = last ? dst : (char *)workspace + (p & 1) * half;
+        rc = tab_apply_impl(adjoint, tabs[plan.dim[p]], plan.npre[p], plan.npost[p], last ? alpha : 1.0, in,
+                            last ? beta : 0.0, out, variant, st);
+        if (rc != LI_OK) return rc;
+        in = out;
+    }
+    return LI_OK;
+}
+
+}  // namespace li
+
+extern "C" {
+
+int li_sep_workspace_bytes(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other,
+                           int64_t nbatch, size_t *bytes)
+{
+    LI_REQUIRE(bytes, LI_ERR_ARG, "null argument");
+    li::SepPlan plan;
+    int rc = li::make_plan(adjoint, ndim, tabs, dims_other, nbatch, &plan);
+    if (rc != LI_OK) return rc;
+    int dtype = LI_F32;
+    for (int k = 0; k < ndim; ++k)
+        if (tabs[k]) dtype = tabs[k]->dtype;
+    size_t half = 0;
+    return li::sep_workspace(plan, dtype, bytes, &half);
+}
+
+int li_sep_apply(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other, int64_t nbatch,
+                 double alpha, const void *src_dev, double beta, void *dst_dev, void *workspace_dev,
+                 size_t workspace_bytes, int variant, void *stream)
+{
+    return li::sep_apply_impl(adjoint, ndim, tabs, dims_other, nbatch, alpha, src_dev, beta, dst_dev, workspace_dev,
+                              workspace_bytes, variant, li::as_stream(stream));
+}
+
+int li_sep_apply_host(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other, int64_t nbatch,
+                      double alpha, const void *src_host, double beta, void *dst_host, int variant, void *stream)
+{
+    LI_REQUIRE(src_host && dst_host, LI_ERR_ARG, "null argument");
+    cudaStream_t st = li::as_stream(stream);
+    li::SepPlan plan;
+    int rc = li::make_plan(adjoint, ndim, tabs, dims_other, nbatch, &plan);
+    if (rc != LI_OK) return rc;
+    int dtype = LI_F32;
+    for (int k = 0; k < ndim; ++k)
+        if (tabs[k]) dtype = tabs[k]->dtype;
+    if (plan.npass == 0) return LI_OK;
+    const size_t es = li::dtype_size(dtype);
+    const size_t nin = (size_t)plan.in_elems * es, nout = (size_t)plan.out_elems[plan.npass - 1] * es;
+    size_t wsb = 0, half = 0;
+    li::sep_workspace(plan, dtype, &wsb, &half);
+    void *dsrc = nullptr, *ddst = nullptr, *ws = nullptr;
+    cudaError_t e = cudaMalloc(&dsrc, nin ? nin : 1);
+    if (e == cudaSuccess) e = cudaMalloc(&ddst, nout ? nout : 1);
+    if (e == cudaSuccess && wsb) e = cudaMalloc(&ws, wsb);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dsrc, src_host, nin, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && beta != 0.0) e = cudaMemcpyAsync(ddst, dst_host, nout, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        rc = li::sep_apply_impl(adjoint, ndim, tabs, dims_other, nbatch, alpha, dsrc, beta, ddst, ws, wsb, variant, st);
+    if (e == cudaSuccess && rc == LI_OK) e = cudaMemcpyAsync(dst_host, ddst, nout, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dsrc);
+    cudaFree(ddst);
+    cudaFree(ws);
+    if (e != cudaSuccess) {
+        li::set_error("host-staged separable apply failed: %s", cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? LI_ERR_NOMEM : LI_ERR_CUDA;
+    }
+    return rc;
+}
+
+// 1-D on-the-fly: coefficients are generated on the device for this call only.
+int li_otf1d_apply(int adjoint, const li_kernel_desc *ker, const void *x_dev, int64_t n, int64_t len, double alpha,
+                   const void *src_dev, double beta, void *dst_dev, int variant, void *stream)
+{
+    LI_REQUIRE(ker && dst_dev, LI_ERR_ARG, "null argument");
+    cudaStream_t st = li::as_stream(stream);
+    if (n == 0) return adjoint ? li::vscale_impl(ker->dtype, dst_dev, len, beta, st) : LI_OK;
+    li_table *t = nullptr;
+    int rc = li::table_create_impl(ker, x_dev, n, len, st, &t);
+    if (rc != LI_OK) return rc;
+    rc = li::tab_apply_impl(adjoint, t, 1, 1, alpha, src_dev, beta, dst_dev, variant, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    li_table_destroy(t);
+    if (rc == LI_OK && e != cudaSuccess) {
+        li::set_error("on-the-fly apply failed: %s", cudaGetErrorString(e));
+        rc = LI_ERR_CUDA;
+    }
+    return rc;
+}
+
+int li_sep2d_otf_apply(int adjoint, const li_kernel_desc *ker1, const void *x1_dev, int64_t n1,
+                       const li_kernel_desc *ker2, const void *x2_dev, int64_t n2, int64_t m1, int64_t m2,
+                       int64_t nbatch, double alpha, const void *src_dev, double beta, void *dst_dev, void *stream)
+{
+    LI_REQUIRE(ker1 && ker2 && dst_dev, LI_ERR_ARG, "null argument");
+    LI_REQUIRE(ker1->dtype == ker2->dtype, LI_ERR_ARG, "kernels must share one floating-point type");
+    cudaStream_t st = li::as_stream(stream);
+    li_table *t[2] = {nullptr, nullptr};
+    int rc = li::table_create_impl(ker1, x1_dev, n1, m1, st, &t[0]);
+    if (rc == LI_OK) rc = li::table_create_impl(ker2, x2_dev, n2, m2, st, &t[1]);
+    void *ws = nullptr;
+    size_t wsb = 0;
+    if (rc == LI_OK) rc = li_sep_workspace_bytes(adjoint, 2, t, nullptr, nbatch, &wsb);
+    if (rc == LI_OK && wsb) {
+        cudaError_t e = cudaMalloc(&ws, wsb);
+        if (e != cudaSuccess) {
+            li::set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
+            rc = LI_ERR_NOMEM;
+        }
+    }
+    if (rc == LI_OK)
+        rc = li::sep_apply_impl(adjoint, 2, t, nullptr, nbatch, alpha, src_dev, beta, dst_dev, ws, wsb,
+                                LI_VARIANT_AUTO, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(ws);
+    li_table_destroy(t[0]);
+    li_table_destroy(t[1]);
+    if (rc == LI_OK && e != cudaSuccess) {
+        li::set_error("on-the-fly separable apply failed: %s", cudaGetErrorString(e));
+        rc = LI_ERR_CUDA;
+    }
+    return rc;
+}
+
+}  // extern "C"

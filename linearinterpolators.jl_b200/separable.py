@@ -1,0 +1,108 @@
+"""Separable operators: fused product of table-backed factors (``li_sep_apply``) and the 2-D on-the-fly
+``apply!(alpha, P, ker1, x1, ker2, x2, src, beta, dst)`` of src/separable.jl:56-162."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _arrays as ar
+from . import _lib
+from .mapping import Adjoint, Direct, check_dst, check_same_kind
+
+_WS = {}
+
+
+def _workspace(like, nbytes: int):
+    """Grow-only device scratch for the unfused multi-pass path (one per device/kind)."""
+    if nbytes == 0:
+        return None, 0
+    key = ("torch", str(like.device)) if ar.is_torch(like) else ("raw",)
+    ws = _WS.get(key)
+    if ws is None or ws[1] < nbytes:
+        buf = ar.empty_like_kind(like, (nbytes // 4 + 1,), np.float32) if ar.is_device(like) else None
+        ws = (buf, nbytes)
+        _WS[key] = ws
+    return ws[0], nbytes
+
+
+def sep_apply_tables(adjoint: bool, tabs, alpha, x, beta, y, owner=None, nbatch_dims: int = 0,
+                     variant=_lib.VARIANT_AUTO):
+    """``y <- alpha * (A_1*...*A_n or its adjoint) * x + beta*y`` for per-dimension tables ``tabs`` (``None`` leaves a
+    dimension untouched).  Trailing ``nbatch_dims`` dimensions of ``x`` are batch dimensions."""
+    dtype = next(t.dtype for t in tabs if t is not None)
+    x = ar.to_colmajor(x, dtype)
+    xs = ar.shape_of(x)
+    n = len(tabs)
+    if len(xs) != n + nbatch_dims:
+        raise _lib.DimensionMismatch("array rank does not match the separable operator")
+    oshape = list(xs)
+    other = (C.c_int64 * n)()
+    for k, t in enumerate(tabs):
+        other[k] = xs[k]
+        if t is not None:
+            nin, nout = (t.nrows, t.ncols) if adjoint else (t.ncols, t.nrows)
+            if xs[k] != nin:
+                raise _lib.DimensionMismatch(f"dimension {k + 1} of source must be {nin}")
+            oshape[k] = nout
+    nbatch = int(np.prod(xs[n:], dtype=np.int64))
+    check_dst(y, tuple(oshape), dtype)
+    check_same_kind(x, y)
+    handles = (C.c_void_p * n)(*[t.handle if t is not None else None for t in tabs])
+    if ar.is_device(y):
+        need = C.c_size_t()
+        _lib.check(_lib.lib.li_sep_workspace_bytes(int(adjoint), n, handles, other, nbatch, C.byref(need)))
+        ws, wsb = _workspace(y, int(need.value))
+        _lib.check(_lib.lib.li_sep_apply(int(adjoint), n, handles, other, nbatch, float(alpha), ar.data_ptr(x),
+                                         float(beta), ar.data_ptr(y), ar.data_ptr(ws) if ws is not None else None,
+                                         wsb, variant, ar.current_stream(y)))
+    else:
+        _lib.check(_lib.lib.li_sep_apply_host(int(adjoint), n, handles, other, nbatch, float(alpha), ar.data_ptr(x),
+                                              float(beta), ar.data_ptr(y), variant, 0))
+    return y
+
+
+def sep2d_otf_apply(alpha, P, ker1, x1, ker2, x2, src, beta, dst):
+    """src/separable.jl:56-162.  Coefficients are evaluated on the device for this call only."""
+    T = ker1.T
+    if ker2.T != T:
+        raise TypeError("kernels must have the same floating-point type")
+    adjoint = P is Adjoint
+    src = ar.to_colmajor(src, T)
+    n1 = int(np.prod(ar.shape_of(x1)))
+    n2 = int(np.prod(ar.shape_of(x2)))
+    ss, ds = ar.shape_of(src), ar.shape_of(dst)
+    if len(ss) != 2 or len(ds) != 2:
+        raise TypeError("source and destination must be 2-dimensional")
+    if adjoint:
+        assert ss == (n1, n2), "size(src) == (length(x1), length(x2))"          # :143
+        m1, m2 = ds
+    else:
+        assert ds == (n1, n2), "size(dst) == (length(x1), length(x2))"          # :78
+        m1, m2 = ss
+    check_dst(dst, ds, T)
+    check_same_kind(src, dst)
+    dev = ar.is_device(dst)
+    stream = ar.current_stream(dst) if dev else 0
+
+    def dev_vec(x):
+        if ar.is_device(x):
+            if ar.np_dtype_of(x) != T:
+                raise TypeError("device positions must have the kernel's floating-point type")
+            return x
+        return ar.to_device(np.ascontiguousarray(np.asarray(x).ravel(), dtype=T),
+                            device=dst.device if ar.is_torch(dst) else None)
+
+    dx1, dx2 = dev_vec(x1), dev_vec(x2)
+    if dev:
+        dsrc, ddst = src, dst
+    else:
+        dsrc = ar.to_device(src)
+        ddst = ar.empty_like_kind(dsrc, ds, T) if float(beta) == 0.0 else ar.to_device(dst)
+    _lib.check(_lib.lib.li_sep2d_otf_apply(int(adjoint), C.byref(ker1.desc()), ar.data_ptr(dx1), n1,
+                                           C.byref(ker2.desc()), ar.data_ptr(dx2), n2, m1, m2, 1, float(alpha),
+                                           ar.data_ptr(dsrc), float(beta), ar.data_ptr(ddst),
+                                           ar.current_stream(ddst) if not dev else stream))
+    if not dev:
+        dst[...] = ar.to_host(ddst)
+    return dst

@@ -1,0 +1,371 @@
+"""GPU parity tests: the CUDA path (through the Python host mirror -> C ABI -> libli_b200.so) against
+the CPU oracle on identical inputs.  Tables must match bit for bit; interpolated values within
+1e-6 (Float32) / 1e-12 (Float64) relative, as stated in BASELINE.json."""
+import numpy as np
+import pytest
+
+import li_oracle as O
+from util import (CONDITIONS, DTYPES, KERNEL_IDS, KERNELS, assert_close, hostile_positions, oracle_kernel,
+                  product_kernel)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def li():
+    import li_b200
+    return li_b200
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("entry", KERNELS, ids=KERNEL_IDS)
+@pytest.mark.parametrize("cname,cond", CONDITIONS)
+@pytest.mark.parametrize("T", DTYPES)
+def test_tables_bit_exact(li, entry, cname, cond, T):
+    rng = np.random.default_rng(42)
+    for ncols in (1, 2, 5, 11, 300):
+        x = hostile_positions(ncols, T, rng)
+        ok = O.kernel(entry[1], entry[2], cond, entry[3])
+        J, W = O.maketable(ok, x, ncols, T)
+        A = li.TabulatedInterpolator(T, product_kernel(li, entry, cond, T), x, ncols)
+        assert A.J.dtype == np.int64 and A.W.dtype == T
+        assert np.array_equal(A.J, J), "index table differs"
+        assert np.array_equal(A.W.view(np.uint32 if T == np.float32 else np.uint64),
+                              W.view(np.uint32 if T == np.float32 else np.uint64)), "weight table differs in bits"
+
+
+@pytest.mark.parametrize("T", DTYPES)
+def test_inexact_error(li, T):
+    lin = li.LinearSpline(T)
+    for bad in (np.nan, 1e19, -1e19, np.inf):
+        with pytest.raises(li.InexactError):
+            li.TabulatedInterpolator(lin, np.array([1.0, bad, 2.0], dtype=T), 5)
+    A = li.TabulatedInterpolator(li.SafeFlat(lin), np.array([1e30, -np.inf], dtype=T), 5)
+    assert A.J.tolist() == [[5, 1], [5, 1]]
+    with pytest.raises(li.InexactError):
+        li.TabulatedInterpolator(li.SafeFlat(lin), np.array([np.nan], dtype=T), 5)
+
+
+def test_getcoefs(li):
+    # test/runtests.jl:90-98 positions + SURVEY Appendix A examples
+    cr = li.CatmullRomSpline(np.float64)
+    assert li.getcoefs(cr, 5, 0.5) == (1, 1, 1, 2, -1 / 16, 9 / 16, 9 / 16, -1 / 16)
+    crs = li.SafeFlat(cr)
+    assert li.getcoefs(crs, 5, -1e-300) == (1, 1, 1, 1, 0, 0, 0, 1)
+    assert li.getcoefs(crs, 5, 6.0000001) == (5, 5, 5, 5, 1, 0, 0, 0)
+    for x in (0, 0.1, -1.2):
+        ref = O.getcoefs(O.kernel(O.CATMULLROM, 4), 4, x, np.float64)
+        got = li.getcoefs(cr, 4, x)
+        assert got[:4] == tuple(ref[0]) and got[4:] == tuple(ref[1])
+
+
+# ------------------------------------------------------------------------------------------------
+def _data():
+    sub = 3
+    x = np.linspace(-1.0, 1.0, 100 * sub + 1)
+    xsub = x[::sub]
+    y = np.cos(2 * x * (x + 2))
+    return x, xsub, y, y[::sub], np.linspace(1.0, float(len(xsub)), len(x))
+
+
+def distance(a, b):
+    return float(np.mean(np.abs(np.asarray(a) - np.asarray(b))))
+
+
+def test_reference_suite_unidimensional(li):
+    # test/runtests.jl:15-49 verbatim, through the product API
+    ker = li.LinearSpline(np.float32)
+    src = np.array([0, 0, 1, 0, 0])
+    x = np.linspace(-1, 7, 81)
+    out = li.apply(ker, x, src)
+    assert out.dtype == np.float32
+    assert out[x == 2.5][0] == 0.5
+    out2 = np.empty_like(out)
+    li.apply_b(out2, ker, x, src)
+    assert np.array_equal(out2, out)
+    li.apply_b(2, li.Direct, ker, x, src, 0, out2)
+    assert np.array_equal(out2, 2 * out)
+    out2[:] = 1
+    li.apply_b(1, li.Direct, ker, x, src, 2, out2)
+    assert np.array_equal(out2, out + 2)
+    out2[:] = 3
+    li.apply_b(0, li.Direct, ker, x, src, 2, out2)
+    assert np.all(out2 == 6)
+    adj = li.apply(li.Adjoint, ker, x, out, len(src))
+    adj2 = np.empty_like(adj)
+    li.apply_b(2, li.Adjoint, ker, x, out, 0, adj2)
+    np.testing.assert_allclose(adj2, 2 * adj, rtol=1e-6)
+    adj2[:] = 1
+    li.apply_b(1, li.Adjoint, ker, x, out, 2, adj2)
+    np.testing.assert_allclose(adj2, adj + 2, rtol=1e-6)
+    adj2[:] = 3
+    li.apply_b(0, li.Adjoint, ker, x, out, 2, adj2)
+    assert np.all(adj2 == 6)
+
+
+REF_KERNELS = [k for k in KERNELS if k[0] in ("Rectangular", "Linear", "Quadratic", "Cubic", "CatmullRom",
+                                               "Keys(-0.4)", "MitchellNetravali", "Lanczos4", "Lanczos6")]
+
+
+@pytest.mark.parametrize("entry", REF_KERNELS, ids=[k[0] for k in REF_KERNELS])
+@pytest.mark.parametrize("cname,cond", CONDITIONS)
+def test_reference_suite_tabulated_and_sparse(li, entry, cname, cond):
+    # test/runtests.jl:100-137
+    x, xsub, y, ysub, t = _data()
+    tol = 0.02 if entry[1] == O.RECTANGULAR else 0.006
+    ker = product_kernel(li, entry, cond, np.float64)
+    Tb = li.TabulatedInterpolator(ker, t, len(xsub))
+    assert distance(Tb(ysub), Tb * ysub) <= 0
+    assert distance(Tb * ysub, y) <= tol
+    assert distance(Tb * ysub, li.apply(ker, t, ysub)) <= 1e-15
+    Sp = li.SparseInterpolator(ker, t, len(xsub))
+    assert distance(Sp(ysub), Sp * ysub) <= 1e-15
+    assert distance(Sp(ysub), Tb(ysub)) <= 1e-15
+    assert distance(Sp(ysub), y) <= tol
+    assert distance(Sp(ysub), li.apply(ker, t, ysub)) <= 1e-15
+    # and against the oracle on the same inputs
+    J, W = O.maketable(oracle_kernel(entry, cond), t, len(xsub), np.float64)
+    assert_close(Tb * ysub, O.tab_direct(J, W, len(xsub), 1, ysub), np.float64)
+
+
+def test_reference_suite_deprecation(li):
+    x, xsub, y, ysub, t = _data()
+    with pytest.warns(DeprecationWarning):
+        li.SparseInterpolator(np.float32, li.RectangularSpline(), t, len(xsub))   # test/runtests.jl:134-136
+
+
+def test_reference_suite_affine_adjoint_identity(li):
+    # test/runtests.jl:139-158
+    rng = np.random.default_rng(5)
+    rows, cols = (11, 16), (10, 15)
+    c = (5.6, 6.4)
+    R = c + li.rotate(li.AffineTransform2D() - c, 0.2)
+    kerlist = (li.RectangularSpline(), li.LinearSpline(), li.CatmullRomSpline())
+    for ker1 in kerlist:
+        for ker2 in kerlist:
+            A = li.TwoDimensionalTransformInterpolator(rows, cols, ker1, ker2, R)
+            x = np.asfortranarray(rng.standard_normal(cols))
+            y = np.asfortranarray(rng.standard_normal(rows))
+            np.testing.assert_allclose(li.vdot(A * x, y), li.vdot(x, A.adj * y), rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T", DTYPES)
+@pytest.mark.parametrize("device", [False, True], ids=["host", "device"])
+def test_tab_apply_nd(li, T, device):
+    rng = np.random.default_rng(11)
+    shape = (37, 19, 6)
+    for entry in (KERNELS[1], KERNELS[4], KERNELS[9]):
+        for d in (1, 2, 3):
+            ncols = shape[d - 1]
+            xs = np.sort(rng.uniform(-2, ncols + 3, 53)) if d != 2 else rng.uniform(-2, ncols + 3, 53)
+            ok = oracle_kernel(entry, O.FLAT)
+            J, W = O.maketable(ok, xs.astype(T), ncols, T)
+            A = li.TabulatedInterpolator(T, d, product_kernel(li, entry, O.FLAT, T), xs, ncols)
+            src = np.asfortranarray(rng.standard_normal(shape).astype(T))
+            for alpha, beta in ((1, 0), (2.5, 0), (1, 1), (-0.5, 2), (0, 3), (0, 0)):
+                ref0 = np.asfortranarray(rng.standard_normal(
+                    tuple(53 if i == d - 1 else n for i, n in enumerate(shape))).astype(T))
+                ref = O.tab_direct(J, W, ncols, d, src, alpha, beta, ref0.copy(order="F"))
+                if device:
+                    dy = li.to_device(ref0)
+                    li.apply_b(alpha, li.Direct, A, li.to_device(src), False, beta, dy)
+                    got = li.to_host(dy)
+                else:
+                    got = ref0.copy(order="F")
+                    li.apply_b(alpha, li.Direct, A, src, False, beta, got)
+                assert_close(got, ref, T, factor=4)
+                # adjoint, deterministic gather and atomic variants
+                ysrc = np.asfortranarray(rng.standard_normal(ref.shape).astype(T))
+                dst0 = np.asfortranarray(rng.standard_normal(shape).astype(T))
+                refa = O.tab_adjoint(J, W, ncols, d, ysrc, alpha, beta, dst0.copy(order="F"))
+                for variant in (li.VARIANT_GATHER, li.VARIANT_ATOMIC):
+                    A.variant = variant
+                    if device:
+                        dd = li.to_device(dst0)
+                        li.apply_b(alpha, li.Adjoint, A, li.to_device(ysrc), False, beta, dd)
+                        gota = li.to_host(dd)
+                    else:
+                        gota = dst0.copy(order="F")
+                        li.apply_b(alpha, li.Adjoint, A, ysrc, False, beta, gota)
+                    assert_close(gota, refa, T, factor=8)
+                A.variant = li.VARIANT_AUTO
+
+
+def test_beta_zero_never_reads_dst(li):
+    T = np.float32
+    A = li.TabulatedInterpolator(T, li.CatmullRomSpline(T), np.linspace(1, 9, 33), 9)
+    src = np.arange(9, dtype=T)
+    y = np.full(33, np.nan, dtype=T)
+    li.apply_b(1, li.Direct, A, src, False, 0, y)
+    assert np.all(np.isfinite(y))
+    z = np.full(9, np.nan, dtype=T)
+    li.apply_b(1, li.Adjoint, A, y, False, 0, z)
+    assert np.all(np.isfinite(z))
+
+
+def test_gather_adjoint_is_deterministic(li):
+    T = np.float32
+    rng = np.random.default_rng(2)
+    xs = rng.uniform(-5, 70, 5000)   # unsorted, many clamped rows -> heavy edge columns
+    A = li.TabulatedInterpolator(T, li.LanczosKernel(T, 6), xs, 64)
+    y = li.to_device(rng.standard_normal(5000).astype(T))
+    outs = [li.to_host(A.adj * y) for _ in range(3)]
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    J, W = O.maketable(O.kernel(O.LANCZOS, 6), xs.astype(T), 64, T)
+    assert_close(outs[0], O.tab_adjoint(J, W, 64, 1, li.to_host(y)), T, factor=50)
+
+
+def test_imported_arbitrary_table(li):
+    # user-defined tables (not window-shaped): generic gather path
+    rng = np.random.default_rng(9)
+    T = np.float64
+    S, nrows, ncols = 3, 40, 17
+    J = rng.integers(1, ncols + 1, size=(S, nrows))
+    W = rng.standard_normal((S, nrows))
+    A = li.TabulatedInterpolator.from_tables(J, W, ncols)
+    assert not A.table.windowed
+    x = rng.standard_normal(ncols)
+    assert_close(A * x, O.tab_direct(np.asfortranarray(J), np.asfortranarray(W), ncols, 1, x), T)
+    y = rng.standard_normal(nrows)
+    assert_close(A.adj * y, O.tab_adjoint(np.asfortranarray(J), np.asfortranarray(W), ncols, 1, y), T, factor=4)
+    with pytest.raises(li.ErrorException):
+        li.TabulatedInterpolator.from_tables(J + ncols, W, ncols)          # out of bound index
+
+
+def test_complex_data(li):
+    rng = np.random.default_rng(4)
+    T = np.float64
+    A = li.TabulatedInterpolator(T, 2, li.CubicSpline(T), np.linspace(0, 8, 21), 7)
+    z = np.asfortranarray(rng.standard_normal((5, 7)) + 1j * rng.standard_normal((5, 7)))
+    J, W = O.maketable(O.kernel(O.CUBIC, 4), np.linspace(0, 8, 21), 7, T)
+    out = A * z
+    assert out.dtype == np.complex128 and out.shape == (5, 21)
+    ref = O.tab_direct(J, W, 7, 2, z.real.copy(order="F")) + 1j * O.tab_direct(J, W, 7, 2, z.imag.copy(order="F"))
+    assert_close(out.real, ref.real, T)
+    assert_close(out.imag, ref.imag, T)
+
+
+def test_error_behaviour(li):
+    T = np.float64
+    A = li.TabulatedInterpolator(li.LinearSpline(T), np.linspace(1, 5, 9), 5)
+    with pytest.raises(li.ErrorException):            # src/tabulated.jl:233
+        li.vcreate(li.Direct, A, np.zeros((5, 3)))
+    with pytest.raises(li.DimensionMismatch):         # src/tabulated.jl:342-343
+        A * np.zeros(6)
+    with pytest.raises(li.DimensionMismatch):
+        li.apply_b(1, li.Direct, A, np.zeros(5), False, 0, np.zeros(8))
+    with pytest.raises(li.ErrorException):            # src/tabulated.jl:310
+        li.apply(li.Direct, A, 3, np.zeros((5, 3)))
+    with pytest.raises(li.ErrorException):            # src/tabulated.jl:83-84,95-96
+        li.TabulatedInterpolator(li.LinearSpline(T), np.linspace(1, 5, 9), 0)
+    B = li.SparseUnidimensionalInterpolator(li.LinearSpline(T), 2, np.linspace(1, 5, 9), 5)
+    with pytest.raises(li.DimensionMismatch):         # src/sparse.jl:646-651
+        B * np.zeros((5, 4))
+    with pytest.raises(li.ArgumentError):             # src/sparse.jl:577
+        li.SparseUnidimensionalInterpolator(li.LinearSpline(T), 1, np.linspace(1, 5, 9), 0)
+    Sp = li.SparseInterpolator(li.LinearSpline(T), np.ones((3, 4)), 5)
+    with pytest.raises(li.ErrorException):            # src/sparse.jl:176-179
+        Sp * np.zeros(4)
+    assert (Sp * np.zeros(5)).shape == (3, 4)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T", DTYPES)
+def test_sparse_interpolator_nd_positions_and_grid(li, T):
+    # test/benchmarks.jl:52-61 shape: 2-D positions, range grid
+    rng = np.random.default_rng(8)
+    n1, n2, n = 30, 20, 25
+    pos = np.array([[1.1 * i + 0.2 * j for j in range(1, n2 + 1)] for i in range(1, n1 + 1)])
+    grd = li.Range(pos.min(), pos.max(), length=n)
+    A = li.SparseInterpolator(li.CatmullRomSpline(T), pos, grd)
+    f = O.fractional_index(pos, grd.first, grd.step, grd.last, n, T)
+    J, W = O.maketable(O.kernel(O.CATMULLROM, 4), f, n, T)
+    assert np.array_equal(A.J, J.reshape(-1, order="F")) and np.array_equal(A.C, W.reshape(-1, order="F"))
+    x = rng.standard_normal(n).astype(T)
+    out = A * x
+    assert out.shape == (n1, n2)
+    assert_close(out.reshape(-1, order="F"), O.tab_direct(J, W, n, 1, x), T)
+    y = np.asfortranarray(rng.standard_normal((n1, n2)).astype(T))
+    assert_close(A.adj * y, O.tab_adjoint(J, W, n, 1, y.reshape(-1, order="F")), T, factor=30)
+    assert A.sparse().shape == (n1 * n2, n)
+
+
+@pytest.mark.parametrize("T", DTYPES)
+def test_separable_composition_2d(li, T):
+    # test/benchmarks.jl:23-49: H = A1*A2 with SparseUnidimensionalInterpolator, forward and adjoint
+    rng = np.random.default_rng(21)
+    n1, n2, m1, m2 = 300, 200, 43, 29
+    ker = li.CatmullRomSpline(T)
+    A1 = li.SparseUnidimensionalInterpolator(ker, 1, np.arange(1, n1 + 1), li.Range(1, n1, length=m1))
+    A2 = li.SparseUnidimensionalInterpolator(ker, 2, np.arange(1, n2 + 1), li.Range(1, n2, length=m2))
+    H = A1 * A2
+    ok = O.kernel(O.CATMULLROM, 4)
+    J1, W1 = O.maketable(ok, O.fractional_index(np.arange(1, n1 + 1), 1, (n1 - 1) / (m1 - 1), n1, m1, T), m1, T)
+    J2, W2 = O.maketable(ok, O.fractional_index(np.arange(1, n2 + 1), 1, (n2 - 1) / (m2 - 1), n2, m2, T), m2, T)
+    x = np.asfortranarray(rng.standard_normal((m1, m2)).astype(T))
+    ref = O.tab_direct(J1, W1, m1, 1, O.tab_direct(J2, W2, m2, 2, x))
+    for xx in (x, li.to_device(x)):
+        assert_close(li.to_host(H * xx), ref, T, factor=4)
+        assert_close(li.to_host((A2 * A1) * xx), ref, T, factor=4)
+    y = np.asfortranarray(rng.standard_normal((n1, n2)).astype(T))
+    refa = O.tab_adjoint(J2, W2, m2, 2, O.tab_adjoint(J1, W1, m1, 1, y, skip_zero=False), skip_zero=False)
+    for yy in (y, li.to_device(y)):
+        assert_close(li.to_host(H.adj * yy), refa, T, factor=16)
+    # alpha/beta through the composition
+    out = np.asfortranarray(rng.standard_normal((n1, n2)).astype(T))
+    want = 0.5 * ref.astype(np.float64) + 2 * out.astype(np.float64)
+    li.apply_b(0.5, li.Direct, H, x, False, 2, out)
+    assert_close(out, want, T, factor=8)
+    np.testing.assert_allclose(li.vdot(H * x, y), li.vdot(x, H.adj * y), rtol=2e-5 if T == np.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("T", DTYPES)
+def test_sep2d_on_the_fly(li, T):
+    rng = np.random.default_rng(17)
+    m1, m2, n1, n2 = 40, 33, 97, 71
+    e1, e2 = KERNELS[4], KERNELS[8]
+    x1 = np.linspace(-1.0, m1 + 2.0, n1).astype(T)
+    x2 = np.linspace(0.5, m2 + 0.5, n2).astype(T)
+    src = np.asfortranarray(rng.standard_normal((m1, m2)).astype(T))
+    k1, k2 = product_kernel(li, e1, O.FLAT, T), product_kernel(li, e2, O.SAFEFLAT, T)
+    o1, o2 = oracle_kernel(e1, O.FLAT), oracle_kernel(e2, O.SAFEFLAT)
+    for alpha, beta in ((1, 0), (0.5, 2), (0, 2)):
+        dst0 = np.asfortranarray(rng.standard_normal((n1, n2)).astype(T))
+        ref = O.sep2d(False, o1, x1, o2, x2, src, (n1, n2), T, alpha, beta, dst0.copy(order="F"))
+        got = dst0.copy(order="F")
+        li.apply_b(alpha, li.Direct, k1, x1, k2, x2, src, beta, got)
+        assert_close(got, ref, T, factor=8)
+        y = np.asfortranarray(rng.standard_normal((n1, n2)).astype(T))
+        d0 = np.asfortranarray(rng.standard_normal((m1, m2)).astype(T))
+        refa = O.sep2d(True, o1, x1, o2, x2, y, (m1, m2), T, alpha, beta, d0.copy(order="F"))
+        gota = d0.copy(order="F")
+        li.apply_b(alpha, li.Adjoint, k1, x1, k2, x2, y, beta, gota)
+        assert_close(gota, refa, T, factor=32)
+
+
+@pytest.mark.parametrize("T", DTYPES)
+def test_affine(li, T):
+    rng = np.random.default_rng(31)
+    rows, cols = (61, 47), (50, 45)
+    R = (25.3, 22.1) + li.rotate(0.7 * li.AffineTransform2D(T=T) - (30.0, 24.0), 0.2)
+    Rc = np.array(li.AffineTransform2D(*R.coefs(), T=T).coefs())
+    for e1, e2 in ((KERNELS[0], KERNELS[1]), (KERNELS[4], KERNELS[4]), (KERNELS[2], KERNELS[8]), (KERNELS[9], KERNELS[9])):
+        k1, k2 = product_kernel(li, e1, O.FLAT, T), product_kernel(li, e2, O.SAFEFLAT, T)
+        o1, o2 = oracle_kernel(e1, O.FLAT), oracle_kernel(e2, O.SAFEFLAT)
+        A = li.TwoDimensionalTransformInterpolator(rows, cols, k1, k2, R)
+        x = np.asfortranarray(rng.standard_normal(cols).astype(T))
+        y = np.asfortranarray(rng.standard_normal(rows).astype(T))
+        assert_close(A * x, O.affine2d(False, o1, o2, Rc, rows, cols, x, T), T, factor=8)
+        assert_close(A.adj * y, O.affine2d(True, o1, o2, Rc, rows, cols, y, T), T, factor=64)
+        for alpha, beta in ((2, 0), (1, 1), (-0.5, 2), (0, 2)):
+            d0 = np.asfortranarray(rng.standard_normal(rows).astype(T))
+            ref = O.affine2d(False, o1, o2, Rc, rows, cols, x, T, alpha, beta, d0.copy(order="F"))
+            got = d0.copy(order="F")
+            li.apply_b(alpha, li.Direct, A, x, False, beta, got)
+            assert_close(got, ref, T, factor=8)
+            c0 = np.asfortranarray(rng.standard_normal(cols).astype(T))
+            refa = O.affine2d(True, o1, o2, Rc, rows, cols, y, T, alpha, beta, c0.copy(order="F"))
+            gota = c0.copy(order="F")
+            li.apply_b(alpha, li.Adjoint, A, y, False, beta, gota)
+            assert_close(gota, refa, T, factor=64)
