@@ -166,6 +166,8 @@ def to_colmajor(x, dtype):
         return x
     if is_torch(x):
         x = x.detach().cpu().numpy()
+    if isinstance(x, np.ndarray) and x.dtype == dtype and x.flags.f_contiguous:
+        return x  # (keeps the pinned-memory subclass)
     a = np.asarray(x)
     if a.dtype == dtype and a.flags.f_contiguous:
         return a

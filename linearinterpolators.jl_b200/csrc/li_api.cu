@@ -41,6 +41,25 @@ int vscale_impl(int dtype, void *y, int64_t n, double beta, cudaStream_t st)
     return LI_OK;
 }
 
+// Grow-only device staging buffers for the host-buffer entry points (one set per host thread):
+// cudaMalloc/cudaFree per call would dominate small applies and serialise the device.
+static thread_local void *g_stage[3] = {nullptr, nullptr, nullptr};
+static thread_local size_t g_stage_bytes[3] = {0, 0, 0};
+
+int staging(int slot, size_t bytes, void **out)
+{
+    if (bytes > g_stage_bytes[slot]) {
+        if (g_stage[slot]) cudaFree(g_stage[slot]);
+        g_stage[slot] = nullptr;
+        g_stage_bytes[slot] = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        LI_CUDA(cudaMalloc(&g_stage[slot], want));
+        g_stage_bytes[slot] = want;
+    }
+    *out = g_stage[slot];
+    return LI_OK;
+}
+
 }  // namespace li
 
 extern "C" {

@@ -122,7 +122,7 @@ int li_sep_workspace_bytes(int adjoint, int ndim, const li_table *const *tabs, c
     for (int k = 0; k < ndim; ++k)
         if (tabs[k]) dtype = tabs[k]->dtype;
     size_t half = 0;
-    return li::sep_workspace(plan, dtype, bytes, &half);
+    return li::sep_workspace(plan, dtype, bytes, &half);  // upper bound (the fused 2-D kernel needs none)
 }
 
 int li_sep_apply(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other, int64_t nbatch,
@@ -150,21 +150,19 @@ int li_sep_apply_host(int adjoint, int ndim, const li_table *const *tabs, const 
     size_t wsb = 0, half = 0;
     li::sep_workspace(plan, dtype, &wsb, &half);
     void *dsrc = nullptr, *ddst = nullptr, *ws = nullptr;
-    cudaError_t e = cudaMalloc(&dsrc, nin ? nin : 1);
-    if (e == cudaSuccess) e = cudaMalloc(&ddst, nout ? nout : 1);
-    if (e == cudaSuccess && wsb) e = cudaMalloc(&ws, wsb);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dsrc, src_host, nin, cudaMemcpyHostToDevice, st);
+    rc = li::staging(0, nin ? nin : 1, &dsrc);
+    if (rc == LI_OK) rc = li::staging(1, nout ? nout : 1, &ddst);
+    if (rc == LI_OK && wsb) rc = li::staging(2, wsb, &ws);
+    if (rc != LI_OK) return rc;
+    cudaError_t e = cudaMemcpyAsync(dsrc, src_host, nin, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && beta != 0.0) e = cudaMemcpyAsync(ddst, dst_host, nout, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess)
         rc = li::sep_apply_impl(adjoint, ndim, tabs, dims_other, nbatch, alpha, dsrc, beta, ddst, ws, wsb, variant, st);
     if (e == cudaSuccess && rc == LI_OK) e = cudaMemcpyAsync(dst_host, ddst, nout, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(dsrc);
-    cudaFree(ddst);
-    cudaFree(ws);
     if (e != cudaSuccess) {
         li::set_error("host-staged separable apply failed: %s", cudaGetErrorString(e));
-        return e == cudaErrorMemoryAllocation ? LI_ERR_NOMEM : LI_ERR_CUDA;
+        return LI_ERR_CUDA;
     }
     return rc;
 }

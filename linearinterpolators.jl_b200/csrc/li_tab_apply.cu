@@ -72,7 +72,7 @@ tab_direct_dn_kernel(const int32_t *__restrict__ J, const T *__restrict__ W, int
     constexpr int SMAX = SC ? SC : LI_MAX_S;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npre) return;
-    const int i0 = blockIdx.y * RB;
+    for (int i0 = blockIdx.y * RB; i0 < nrows; i0 += gridDim.y * RB)
     for (int64_t q = blockIdx.z; q < npost; q += gridDim.z) {
         const T *sp = src + p + q * npre * ncols;
         T *dp = dst + p + q * npre * nrows;
@@ -124,7 +124,7 @@ tab_adjoint_gather_dn_kernel(const int32_t *__restrict__ colptr, const int32_t *
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npre) return;
-    const int j = blockIdx.y;
+    for (int j = blockIdx.y; j < ncols; j += gridDim.y) {
     const int e0 = colptr[j], e1 = colptr[j + 1];
     for (int64_t q = blockIdx.z; q < npost; q += gridDim.z) {
         const T *sp = src + p + q * npre * nrows;
@@ -137,6 +137,7 @@ tab_adjoint_gather_dn_kernel(const int32_t *__restrict__ colptr, const int32_t *
             acc = fma_(W[ent], x, acc);
         }
         *d = acc;
+    }
     }
 }
 
@@ -173,9 +174,8 @@ static int launch_direct(const li_table *t, int64_t npre, int64_t npost, T alpha
     } else {
         constexpr int RB = 4;
         const int threads = npre >= 256 ? 256 : (npre >= 128 ? 128 : (npre >= 64 ? 64 : 32));
-        dim3 grid((unsigned)((npre + threads - 1) / threads), (nrows + RB - 1) / RB,
+        dim3 grid((unsigned)((npre + threads - 1) / threads), std::min((nrows + RB - 1) / RB, 65535),
                   (unsigned)std::min<int64_t>(npost, 65535));
-        LI_REQUIRE(grid.y <= 65535, LI_ERR_UNSUPPORTED, "too many rows for the strided kernel");
         tab_direct_dn_kernel<T, SC, RB><<<grid, threads, 0, st>>>(t->J, (const T *)t->W, t->S, nrows, ncols, npre,
                                                                 npost, alpha, beta, src, dst);
     }
@@ -223,8 +223,8 @@ static int adjoint_T(const li_table *t, int64_t npre, int64_t npost, double alph
                                                              ncols, npost, a, b, (const T *)src, (T *)dst);
     } else {
         const int threads = npre >= 256 ? 256 : (npre >= 128 ? 128 : (npre >= 64 ? 64 : 32));
-        LI_REQUIRE(ncols <= 65535 * 1, LI_ERR_UNSUPPORTED, "too many columns for the strided adjoint kernel");
-        dim3 grid((unsigned)((npre + threads - 1) / threads), ncols, (unsigned)std::min<int64_t>(npost, 65535));
+        dim3 grid((unsigned)((npre + threads - 1) / threads), std::min(ncols, 65535),
+                  (unsigned)std::min<int64_t>(npost, 65535));
         tab_adjoint_gather_dn_kernel<T><<<grid, threads, 0, st>>>(t->colptr, t->tent, (const T *)t->W, t->S, nrows,
                                                                  ncols, npre, npost, a, b, (const T *)src, (T *)dst);
     }
@@ -268,16 +268,14 @@ int li_tab_apply_host(int adjoint, const li_table *t, int64_t npre, int64_t npos
     const size_t nin = (size_t)(npre * npost * (adjoint ? t->nrows : t->ncols)) * es;
     const size_t nout = (size_t)(npre * npost * (adjoint ? t->ncols : t->nrows)) * es;
     void *dsrc = nullptr, *ddst = nullptr;
-    LI_CUDA(cudaMalloc(&dsrc, nin ? nin : 1));
-    cudaError_t e = cudaMalloc(&ddst, nout ? nout : 1);
-    int rc = LI_OK;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dsrc, src_host, nin, cudaMemcpyHostToDevice, st);
+    int rc = li::staging(0, nin ? nin : 1, &dsrc);
+    if (rc == LI_OK) rc = li::staging(1, nout ? nout : 1, &ddst);
+    if (rc != LI_OK) return rc;
+    cudaError_t e = cudaMemcpyAsync(dsrc, src_host, nin, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && beta != 0.0) e = cudaMemcpyAsync(ddst, dst_host, nout, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) rc = li::tab_apply_impl(adjoint, t, npre, npost, alpha, dsrc, beta, ddst, variant, st);
     if (e == cudaSuccess && rc == LI_OK) e = cudaMemcpyAsync(dst_host, ddst, nout, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(dsrc);
-    cudaFree(ddst);
     if (e != cudaSuccess) {
         li::set_error("host-staged apply failed: %s", cudaGetErrorString(e));
         return LI_ERR_CUDA;

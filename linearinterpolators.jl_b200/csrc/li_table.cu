@@ -159,56 +159,40 @@ __global__ void fwd_span_kernel(const int32_t *__restrict__ base, int64_t nrows,
 }
 
 // rowstart[k] = first row i with base[i] + S - 1 >= k  (monotone base), k in [0, ncols];
-// rowstart[ncols] = nrows.  Rows contributing to column k are [rowstart[k], rowend(k)) with
-// rowend(k) = first row with base > k  (for k = ncols-1: nrows, clamped taps included).
+// rowend[k]   = first row i with base[i] > k; rows contributing to column k are
+// [rowstart[k], rowend[k]).  Column 0 also collects the clamped taps of every leading row and
+// column ncols-1 those of every trailing row.  Layout: rowstart[0..ncols], then rowend[0..ncols].
 __global__ void rowstart_kernel(const int32_t *__restrict__ base, int64_t nrows, int S, int ncols,
                                 int32_t *__restrict__ rowstart)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > ncols) return;
-    if (k == ncols) {
-        rowstart[k] = (int32_t)nrows;
-        return;
-    }
-    if (k == 0) {
-        rowstart[0] = 0;  // clamped taps of every leading row land in column 0
-        return;
-    }
-    int64_t lo = 0, hi = nrows;  // first i with base[i] >= k - (S-1)
-    const int target = k - (S - 1);
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (base[mid] >= target)
-            hi = mid;
-        else
-            lo = mid + 1;
-    }
-    rowstart[k] = (int32_t)lo;
+    int32_t *rowend = rowstart + (ncols + 1);
+    // first i with base[i] >= target
+    auto lower = [&](int target) {
+        int64_t lo = 0, hi = nrows;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (base[mid] >= target)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        return (int32_t)lo;
+    };
+    rowstart[k] = k == ncols ? (int32_t)nrows : (k == 0 ? 0 : lower(k - (S - 1)));
+    rowend[k] = k >= ncols - 1 ? (int32_t)nrows : lower(k + 1);
 }
 
-// number of rows feeding an aligned tile of G columns: rowend(k1-1) - rowstart[k0]
-__global__ void adj_rows_kernel(const int32_t *__restrict__ base, const int32_t *__restrict__ rowstart,
-                                int64_t nrows, int ncols, int G, int *out)
+// number of rows feeding an aligned tile of G columns: rowend[k1-1] - rowstart[k0]
+__global__ void adj_rows_kernel(const int32_t *__restrict__ rowstart, int ncols, int G, int *out)
 {
     int tile = blockIdx.x * blockDim.x + threadIdx.x;
     int k0 = tile * G;
     if (k0 >= ncols) return;
     int k1 = min(k0 + G, ncols);  // exclusive
-    int64_t end;
-    if (k1 == ncols) {
-        end = nrows;
-    } else {
-        int64_t lo = 0, hi = nrows;  // first i with base[i] > k1-1
-        while (lo < hi) {
-            int64_t mid = (lo + hi) >> 1;
-            if (base[mid] > k1 - 1)
-                hi = mid;
-            else
-                lo = mid + 1;
-        }
-        end = lo;
-    }
-    atomicMax(out, (int)(end - rowstart[k0]));
+    const int32_t *rowend = rowstart + (ncols + 1);
+    atomicMax(out, (int)(rowend[k1 - 1] - rowstart[k0]));
 }
 
 __global__ void iota_keys_kernel(const int32_t *__restrict__ J, int64_t n, int32_t *__restrict__ keys,
@@ -366,7 +350,7 @@ int table_ensure_rowstart(const li_table *t, cudaStream_t st)
     if (t->rowstart) return LI_OK;
     LI_REQUIRE(t->windowed && t->monotone, LI_ERR_ARG, "rowstart needs a monotone windowed table");
     int32_t *rs = nullptr;
-    LI_CUDA(cudaMalloc(&rs, (t->ncols + 1) * sizeof(int32_t)));
+    LI_CUDA(cudaMalloc(&rs, 2 * (t->ncols + 1) * sizeof(int32_t)));
     rowstart_kernel<<<(unsigned)((t->ncols + 1 + 255) / 256), 256, 0, st>>>(t->base, t->nrows, t->S,
                                                                           (int)t->ncols, rs);
     count_launch();
@@ -439,7 +423,7 @@ int table_adj_rows(const li_table *t, int G, cudaStream_t st, int *rows)
     int v = 0;
     const int ntiles = (int)((t->ncols + G - 1) / G);
     rc = reduce_to_host(st, 0, &v, [&](int *d) {
-        adj_rows_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(t->base, t->rowstart, t->nrows, (int)t->ncols, G, d);
+        adj_rows_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(t->rowstart, (int)t->ncols, G, d);
     });
     if (rc != LI_OK) return rc;
     std::lock_guard<std::mutex> lock(t->mu);
