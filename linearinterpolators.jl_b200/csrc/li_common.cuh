@@ -60,12 +60,13 @@ struct li_table {
     int32_t *base = nullptr;  // [nrows] canonical window base (0-based tap s is clamp(base+s)); valid iff windowed
     bool windowed = false;
     bool monotone = false;
+    int max_step = 1;         // max(base[i+1] - base[i], 1) for monotone tables (1 <=> up-sampling or unit rate)
     // lazily built adjoint helpers (guarded by mu)
     mutable std::mutex mu;
     // generic transposed (CSC) table: entries sorted by (column, row, tap)
     mutable int32_t *colptr = nullptr;  // [ncols+1]
     mutable int32_t *tent = nullptr;    // [nrows*S] entry id e = row*S + tap
-    // monotone windowed tables: rowstart[k] = first row whose window reaches column k  ([ncols+1])
+    // monotone windowed tables: bptr[j] = first row with base >= j-(S-1), j in [0, ncols+S-1] (see li_table.cu)
     mutable int32_t *rowstart = nullptr;
     // cached footprint bounds: key = tile rows G -> max over aligned tiles of (max base - min base)
     mutable std::map<int, int> fwd_span;

@@ -85,10 +85,15 @@ static int dispatch_gen(const li_kernel_desc *ker, const void *pos, int64_t nrow
 // Analysis kernels.
 
 // monotone <=> base[i] <= base[i+1] for all i
+// flag[0] <- 0 unless monotone; flag[1] <- max(base[i+1] - base[i])
 __global__ void monotone_kernel(const int32_t *__restrict__ base, int64_t nrows, int *flag)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i + 1 < nrows && base[i] > base[i + 1]) atomicExch(flag, 0);
+    if (i + 1 < nrows) {
+        const int d = base[i + 1] - base[i];
+        if (d < 0) atomicExch(flag, 0);
+        if (d > 1) atomicMax(flag + 1, d);
+    }
 }
 
 // For imported tables: recover the canonical window base of every row, or flag the table
@@ -158,41 +163,35 @@ __global__ void fwd_span_kernel(const int32_t *__restrict__ base, int64_t nrows,
     if ((threadIdx.x & 31) == 0 && hi >= lo) atomicMax(out, hi - lo);
 }
 
-// rowstart[k] = first row i with base[i] + S - 1 >= k  (monotone base), k in [0, ncols];
-// rowend[k]   = first row i with base[i] > k; rows contributing to column k are
-// [rowstart[k], rowend[k]).  Column 0 also collects the clamped taps of every leading row and
-// column ncols-1 those of every trailing row.  Layout: rowstart[0..ncols], then rowend[0..ncols].
-__global__ void rowstart_kernel(const int32_t *__restrict__ base, int64_t nrows, int S, int ncols,
-                                int32_t *__restrict__ rowstart)
+// bptr[j] = first row i with base[i] >= j - (S-1), j in [0, ncols + S - 1]  (monotone base; canonical bases
+// lie in [-(S-1), ncols-1], so bptr[0] = 0 and bptr[ncols+S-1] = nrows).
+//   rows whose window base equals v      : [bptr[v+S-1], bptr[v+S])
+//   rows contributing to column k        : [bptr[k], bptr[k+S])   (clamped taps included for k = 0, ncols-1)
+__global__ void bptr_kernel(const int32_t *__restrict__ base, int64_t nrows, int S, int ncols,
+                            int32_t *__restrict__ bptr)
 {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > ncols) return;
-    int32_t *rowend = rowstart + (ncols + 1);
-    // first i with base[i] >= target
-    auto lower = [&](int target) {
-        int64_t lo = 0, hi = nrows;
-        while (lo < hi) {
-            int64_t mid = (lo + hi) >> 1;
-            if (base[mid] >= target)
-                hi = mid;
-            else
-                lo = mid + 1;
-        }
-        return (int32_t)lo;
-    };
-    rowstart[k] = k == ncols ? (int32_t)nrows : (k == 0 ? 0 : lower(k - (S - 1)));
-    rowend[k] = k >= ncols - 1 ? (int32_t)nrows : lower(k + 1);
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > ncols + S - 1) return;
+    const int target = j - (S - 1);
+    int64_t lo = 0, hi = nrows;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (base[mid] >= target)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    bptr[j] = (int32_t)lo;
 }
 
-// number of rows feeding an aligned tile of G columns: rowend[k1-1] - rowstart[k0]
-__global__ void adj_rows_kernel(const int32_t *__restrict__ rowstart, int ncols, int G, int *out)
+// number of rows feeding an aligned tile of G columns
+__global__ void adj_rows_kernel(const int32_t *__restrict__ bptr, int S, int ncols, int G, int *out)
 {
     int tile = blockIdx.x * blockDim.x + threadIdx.x;
     int k0 = tile * G;
     if (k0 >= ncols) return;
     int k1 = min(k0 + G, ncols);  // exclusive
-    const int32_t *rowend = rowstart + (ncols + 1);
-    atomicMax(out, (int)(rowend[k1 - 1] - rowstart[k0]));
+    atomicMax(out, (int)(bptr[k1 - 1 + S] - bptr[k0]));
 }
 
 __global__ void iota_keys_kernel(const int32_t *__restrict__ J, int64_t n, int32_t *__restrict__ keys,
@@ -253,9 +252,9 @@ int table_create_impl(const li_kernel_desc *ker, const void *pos_dev, int64_t nr
     li_table *t = nullptr;
     int rc = alloc_table(ker->dtype, ker->S, nrows, ncols, &t);
     if (rc != LI_OK) return rc;
-    int *flags = nullptr;  // [0] inexact, [1] monotone
-    int h_flags[2] = {0, 1};
-    cudaError_t e = cudaMalloc(&flags, 2 * sizeof(int));
+    int *flags = nullptr;  // [0] inexact, [1] monotone, [2] max step of the window base
+    int h_flags[3] = {0, 1, 1};
+    cudaError_t e = cudaMalloc(&flags, sizeof h_flags);
     if (e == cudaSuccess) e = cudaMemcpyAsync(flags, h_flags, sizeof h_flags, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) {
         set_error("cudaMalloc/cudaMemcpy failed: %s", cudaGetErrorString(e));
@@ -286,6 +285,7 @@ int table_create_impl(const li_kernel_desc *ker, const void *pos_dev, int64_t nr
     }
     t->windowed = true;
     t->monotone = h_flags[1] != 0;
+    t->max_step = h_flags[2];
     *out = t;
     return LI_OK;
 }
@@ -350,15 +350,14 @@ int table_ensure_rowstart(const li_table *t, cudaStream_t st)
     if (t->rowstart) return LI_OK;
     LI_REQUIRE(t->windowed && t->monotone, LI_ERR_ARG, "rowstart needs a monotone windowed table");
     int32_t *rs = nullptr;
-    LI_CUDA(cudaMalloc(&rs, 2 * (t->ncols + 1) * sizeof(int32_t)));
-    rowstart_kernel<<<(unsigned)((t->ncols + 1 + 255) / 256), 256, 0, st>>>(t->base, t->nrows, t->S,
-                                                                          (int)t->ncols, rs);
+    LI_CUDA(cudaMalloc(&rs, (t->ncols + t->S) * sizeof(int32_t)));
+    bptr_kernel<<<(unsigned)((t->ncols + t->S + 255) / 256), 256, 0, st>>>(t->base, t->nrows, t->S, (int)t->ncols, rs);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         cudaFree(rs);
-        set_error("rowstart kernel failed: %s", cudaGetErrorString(e));
+        set_error("bptr kernel failed: %s", cudaGetErrorString(e));
         return LI_ERR_CUDA;
     }
     t->rowstart = rs;
@@ -423,7 +422,7 @@ int table_adj_rows(const li_table *t, int G, cudaStream_t st, int *rows)
     int v = 0;
     const int ntiles = (int)((t->ncols + G - 1) / G);
     rc = reduce_to_host(st, 0, &v, [&](int *d) {
-        adj_rows_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(t->rowstart, (int)t->ncols, G, d);
+        adj_rows_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(t->rowstart, t->S, (int)t->ncols, G, d);
     });
     if (rc != LI_OK) return rc;
     std::lock_guard<std::mutex> lock(t->mu);
@@ -473,7 +472,7 @@ int li_table_import(int dtype, int S, int64_t nrows, int64_t ncols, const int64_
     const int64_t n = nrows * S;
     int64_t *dJ = nullptr;
     int *flags = nullptr;
-    int h_flags[3] = {1, 0, 1};  // windowed, out-of-bounds, monotone
+    int h_flags[4] = {1, 0, 1, 1};  // windowed, out-of-bounds, monotone, max step
     cudaError_t e = cudaMalloc(&dJ, n * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaMalloc(&flags, sizeof h_flags);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dJ, J_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, st);
@@ -502,6 +501,7 @@ int li_table_import(int dtype, int S, int64_t nrows, int64_t ncols, const int64_
     }
     t->windowed = h_flags[0] != 0;
     t->monotone = t->windowed && h_flags[2] != 0;
+    t->max_step = h_flags[3];
     *out = t;
     return LI_OK;
 }
