@@ -35,6 +35,9 @@ template <>
 struct VecT<float, 1> { using type = float; };
 template <>
 struct VecT<double, 2> { using type = double2; };
+struct __align__(16) double4a { double x, y, z, w; };   // two 16-byte transactions
+template <>
+struct VecT<double, 4> { using type = double4a; };
 template <>
 struct VecT<double, 1> { using type = double; };
 
@@ -94,21 +97,40 @@ struct SepArgs {
 constexpr int FWD_TO2 = 64;
 constexpr int FWD_NT = 256;
 
-template <typename T, int S1, int S2, int NG, bool PAIR>
-__global__ void __launch_bounds__(FWD_NT)
+template <typename T, int S>
+__device__ __forceinline__ void ld_weights(const T *p, T (&w)[S])
+{
+    // rows of S weights are 16-byte aligned when S*sizeof(T) is a multiple of 16
+    if constexpr ((S * sizeof(T)) % 16 == 0) {
+        constexpr int V = 16 / sizeof(T);
+#pragma unroll
+        for (int k = 0; k < S / V; ++k) {
+            const Pack<T, V> t = ld_pack<T, V>(p + k * V);
+#pragma unroll
+            for (int v = 0; v < V; ++v) w[k * V + v] = t.v[v];
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) w[s] = p[s];
+    }
+}
+
+template <typename T, int S1, int S2, int NG, bool PAIR, bool BETA>
+__global__ void __launch_bounds__(FWD_NT, (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : 2)
 sep2d_fwd_kernel(const SepArgs<T> a)
 {
     constexpr int NT = FWD_NT, TPG = NT / NG, TO1 = 2 * TPG, TO2 = FWD_TO2, RG = TO2 / NG;
     static_assert(NG * RG == TO2 && TO2 <= NT, "bad tiling");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int P1 = a.F1MAX + 1;                          // one spare column: the paired load reads S1+1 taps
-    T *sS = reinterpret_cast<T *>(smem_raw);             // [F2MAX][P1] staged src tile
-    T *sW2 = sS + (size_t)a.F2MAX * P1;                  // [TO2][S2]
+    const int P1 = a.F1MAX;                              // row pitch of the staged tile (multiple of 4, >= footprint + 4)
+    const int R2 = a.F2MAX;                              // staged rows incl. S2 rows of padding
+    T *sS = reinterpret_cast<T *>(smem_raw);             // [R2][P1] staged src tile
+    T *sW2 = sS + (size_t)R2 * P1;                       // [TO2][S2]  alpha * W2
     int *sB2 = reinterpret_cast<int *>(sW2 + TO2 * S2);  // [TO2]
-    int *sCnt = sB2 + TO2;                               // [NG][F2MAX] outputs completed by each source row
+    int *sCnt = sB2 + TO2;                               // [NG][R2] outputs completed by each source row
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     int bid = blockIdx.x;
     const int tile1 = bid % a.tiles1;
     bid /= a.tiles1;
@@ -123,19 +145,37 @@ sep2d_fwd_kernel(const SepArgs<T> a)
     const int rows = min(TO2, a.n2 - i2_0);
     const int lo2 = a.base2[i2_0], F2 = a.base2[i2_0 + rows - 1] + S2 - lo2;
 
-    for (int k = tid; k < NG * a.F2MAX; k += NT) sCnt[k] = 0;
+    for (int k = tid; k < NG * R2; k += NT) sCnt[k] = 0;
     __syncthreads();
     if (tid < rows) {
         const int b = a.base2[i2_0 + tid];
         sB2[tid] = b;
-        atomicAdd(&sCnt[(tid / RG) * a.F2MAX + (b - lo2 + S2 - 1)], 1);
+        atomicAdd(&sCnt[(tid / RG) * R2 + (b - lo2 + S2 - 1)], 1);
     }
-    for (int k = tid; k < rows * S2; k += NT) sW2[k] = a.W2[(int64_t)i2_0 * S2 + k];
+    for (int k = tid; k < rows * S2; k += NT) sW2[k] = a.alpha * a.W2[(int64_t)i2_0 * S2 + k];
 
-    // stage the (clamped) source tile: row r <-> source index clamp(lo2 + r) of dim 2
-    for (int r = warp; r < F2; r += NT / 32) {
-        const T *row = src + (int64_t)clampi(lo2 + r, a.m2 - 1) * a.m1;
-        for (int c = lane; c < F1; c += 32) sS[r * P1 + c] = row[clampi(lo1 + c, a.m1 - 1)];
+    // stage the source tile; column c of the staged tile <-> source column lo1a + c
+    const int lo1a = a.vec_ok ? (lo1 & ~3) : lo1;   // vec_ok: m1 % 4 == 0 and src is 16-byte aligned
+    const int shift1 = lo1 - lo1a;
+    const bool interior = a.vec_ok && lo1a >= 0 && lo1a + P1 <= a.m1 && lo2 >= 0 && lo2 + F2 <= a.m2;
+    if (interior) {
+        // 64 x 4 thread grid: 16-byte loads, no clamping
+        const int cx = tid & 63, ry = tid >> 6;
+        if (cx * 4 < F1 + shift1) {
+            const T *g = src + (int64_t)(lo2 + ry) * a.m1 + lo1a + cx * 4;
+            T *sp = sS + ry * P1 + cx * 4;
+            for (int r = ry; r < F2; r += NT / 64) {
+                st_pack<T, 4>(sp, ld_pack<T, 4>(g));
+                g += (int64_t)(NT / 64) * a.m1;
+                sp += (NT / 64) * P1;
+            }
+        }
+    } else {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int r = warp; r < F2; r += NT / 32) {
+            const T *row = src + (int64_t)clampi(lo2 + r, a.m2 - 1) * a.m1;
+            for (int c = lane; c < F1 + shift1; c += 32) sS[r * P1 + c] = row[clampi(lo1a + c, a.m1 - 1)];
+        }
     }
 
     // per-thread dim-1 taps
@@ -143,7 +183,7 @@ sep2d_fwd_kernel(const SepArgs<T> a)
     const int colA = i1_0 + cA;
     const bool haveA = colA < a.n1, haveB = colA + 1 < a.n1;
     const int iA = min(colA, a.n1 - 1), iB = min(colA + 1, a.n1 - 1);
-    const int offA = a.base1[iA] - lo1, offB = a.base1[iB] - lo1;
+    const int offA = a.base1[iA] - lo1a, offB = a.base1[iB] - lo1a;
     T w1A[S1], w1B[S1];
 #pragma unroll
     for (int s = 0; s < S1; ++s) {
@@ -157,72 +197,70 @@ sep2d_fwd_kernel(const SepArgs<T> a)
     if (!haveA || r0 >= rows) return;
     const int r1 = min(r0 + RG, rows);
     const int rb = sB2[r0] - lo2, re = sB2[r1 - 1] - lo2 + S2;   // source rows of this group
-    const bool vec = a.vec_ok && haveB;
-    int next = r0;                                              // next output row (tile-local) to emit
+    const bool vec = a.vec_ok && haveB;                         // (n1 is even whenever vec_ok)
+    const T *wp = sW2 + r0 * S2;                                // weights of the next output row
+    T *dp = dst + (int64_t)(i2_0 + r0) * a.n1 + colA;           // next output element
+    const int *cp = sCnt + g * R2;
+    const T *pA = sS + offA, *pB = sS + offB;
     T hA[S2], hB[S2];
 #pragma unroll
     for (int s = 0; s < S2; ++s) hA[s] = hB[s] = (T)0;
 
+    // rows [re, rb + ceil((re-rb)/S2)*S2) are padding: they exist in smem, complete no output
     for (int r = rb; r < re; r += S2) {
 #pragma unroll
         for (int u = 0; u < S2; ++u) {
             const int rr = r + u;
-            if (rr < re) {
-                // pass 1: dim 1, from the staged tile
-                const T *p = sS + rr * P1 + offA;
-                T accA, accB;
-                if constexpr (PAIR) {
-                    T v[S1 + 1];
+            // pass 1: dim 1, from the staged tile
+            T accA, accB;
+            if constexpr (PAIR) {
+                const T *p = pA + rr * P1;
+                T v[S1 + 1];
 #pragma unroll
-                    for (int s = 0; s <= S1; ++s) v[s] = p[s];
-                    accA = v[0] * w1A[0];
-                    accB = (shift ? v[1] : v[0]) * w1B[0];
+                for (int s = 0; s <= S1; ++s) v[s] = p[s];
+                accA = v[0] * w1A[0];
+                accB = (shift ? v[1] : v[0]) * w1B[0];
 #pragma unroll
-                    for (int s = 1; s < S1; ++s) {
-                        accA = fmaT(v[s], w1A[s], accA);
-                        accB = fmaT(shift ? v[s + 1] : v[s], w1B[s], accB);
-                    }
+                for (int s = 1; s < S1; ++s) {
+                    accA = fmaT(v[s], w1A[s], accA);
+                    accB = fmaT(shift ? v[s + 1] : v[s], w1B[s], accB);
+                }
+            } else {
+                const T *p = pA + rr * P1, *q = pB + rr * P1;
+                accA = p[0] * w1A[0];
+                accB = q[0] * w1B[0];
+#pragma unroll
+                for (int s = 1; s < S1; ++s) {
+                    accA = fmaT(p[s], w1A[s], accA);
+                    accB = fmaT(q[s], w1B[s], accB);
+                }
+            }
+            hA[u] = accA;
+            hB[u] = accB;
+            // pass 2: emit the output rows whose window [rr-S2+1, rr] is now complete
+            for (int n = cp[rr]; n > 0; --n) {
+                T w2[S2];
+                ld_weights<T, S2>(wp, w2);
+                wp += S2;
+                T oA = hA[(u + 1) % S2] * w2[0], oB = hB[(u + 1) % S2] * w2[0];
+#pragma unroll
+                for (int s = 1; s < S2; ++s) {
+                    oA = fmaT(hA[(u + 1 + s) % S2], w2[s], oA);
+                    oB = fmaT(hB[(u + 1 + s) % S2], w2[s], oB);
+                }
+                if constexpr (BETA) {
+                    oA = fmaT(a.beta, dp[0], oA);
+                    if (haveB) oB = fmaT(a.beta, dp[1], oB);
+                }
+                if (vec) {
+                    Pack<T, 2> o;
+                    o.v[0] = oA, o.v[1] = oB;
+                    st_pack<T, 2>(dp, o);
                 } else {
-                    const T *q = sS + rr * P1 + offB;
-                    accA = p[0] * w1A[0];
-                    accB = q[0] * w1B[0];
-#pragma unroll
-                    for (int s = 1; s < S1; ++s) {
-                        accA = fmaT(p[s], w1A[s], accA);
-                        accB = fmaT(q[s], w1B[s], accB);
-                    }
+                    dp[0] = oA;
+                    if (haveB) dp[1] = oB;
                 }
-                hA[u] = accA;
-                hB[u] = accB;
-                // pass 2: emit the output rows whose window [rr-S2+1, rr] is now complete
-                const int n = sCnt[g * a.F2MAX + rr];
-                for (int k = 0; k < n; ++k, ++next) {
-                    T w2[S2];
-#pragma unroll
-                    for (int s = 0; s < S2; ++s) w2[s] = sW2[next * S2 + s];
-                    T oA = hA[(u + 1) % S2] * w2[0], oB = hB[(u + 1) % S2] * w2[0];
-#pragma unroll
-                    for (int s = 1; s < S2; ++s) {
-                        oA = fmaT(hA[(u + 1 + s) % S2], w2[s], oA);
-                        oB = fmaT(hB[(u + 1 + s) % S2], w2[s], oB);
-                    }
-                    T *d = dst + (int64_t)(i2_0 + next) * a.n1 + colA;
-                    if (a.beta != (T)0) {
-                        oA = fmaT(a.alpha, oA, a.beta * d[0]);
-                        if (haveB) oB = fmaT(a.alpha, oB, a.beta * d[1]);
-                    } else if (a.alpha != (T)1) {
-                        oA *= a.alpha;
-                        oB *= a.alpha;
-                    }
-                    if (vec) {
-                        Pack<T, 2> o;
-                        o.v[0] = oA, o.v[1] = oB;
-                        st_pack<T, 2>(d, o);
-                    } else {
-                        d[0] = oA;
-                        if (haveB) d[1] = oB;
-                    }
-                }
+                dp += a.n1;
             }
         }
     }
@@ -234,6 +272,8 @@ sep2d_fwd_kernel(const SepArgs<T> a)
 //            group in ascending order (coalesced vector loads, a register queue PF rows ahead), adding each
 //            row into S2 accumulators -- the order of the reference's sequential scatter.  When the window
 //            base advances, the oldest accumulator is a finished dst row and goes to shared memory.
+//            The clamped taps of the first/last dst rows are folded into the staged copy of the weights, so
+//            the hot loop has no edge cases.
 //   phase 2 (dim 1): a thread owns one dst column; its taps (one per contributing src column) sit in
 //            registers and are reused for every row.  sT is stored in two parity planes so that the
 //            stride-2 gather of a 2x operator is bank-conflict free.
@@ -242,8 +282,8 @@ constexpr int ADJ_NT = 256;
 constexpr int ADJ_MAXE = 12;  // taps per dst column kept in registers; longer lists use a slow loop
 constexpr int ADJ_PF = 4;     // src rows in flight per thread
 
-template <typename T, int S1, int S2, int NG>
-__global__ void __launch_bounds__(ADJ_NT)
+template <typename T, int S1, int S2, int NG, bool BETA>
+__global__ void __launch_bounds__(ADJ_NT, (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : 2)
 sep2d_adj_kernel(const SepArgs<T> a, const int TD1)
 {
     constexpr int TD2 = ADJ_TD2, NT = ADJ_NT, TPG = NT / NG, PT = 2 * TPG, RG = TD2 / NG, PF = ADJ_PF;
@@ -252,11 +292,12 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1)
     static_assert(NG * RG == TD2, "bad tiling");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R2 = a.F2MAX;                                  // staged src rows per group (multiple of PF)
     T *sT = reinterpret_cast<T *>(smem_raw);                 // [2][TD2][PH] (+skew)
     T *sW1 = sT + 2 * PLANE;                                 // [PT][S1]
-    T *sW2 = sW1 + (size_t)PT * S1;                          // [NG][F2MAX][S2]
-    int *sB1 = reinterpret_cast<int *>(sW2 + (size_t)NG * a.F2MAX * S2);   // [PT]
-    int *sB2 = sB1 + PT;                                     // [NG][F2MAX]
+    T *sW2 = sW1 + (size_t)PT * S1;                          // [NG][R2][S2]  alpha * W2, edge taps folded
+    int *sB1 = reinterpret_cast<int *>(sW2 + (size_t)NG * R2 * S2);   // [PT]
+    int *sB2 = sB1 + PT;                                     // [NG][R2]
 
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -277,11 +318,39 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1)
     const int g = tid / TPG, ct = tid % TPG;
     const int ka = d0 + g * RG, kb = min(ka + RG, d1);      // dst rows owned by this group
     const int i2lo = ka < kb ? a.bp2[ka] : 0, i2hi = ka < kb ? a.bp2[kb - 1 + S2] : 0;
+    const int nrow = i2hi - i2lo;
+    const int nrow_pad = (nrow + PF - 1) / PF * PF;         // <= R2 (host)
 
     for (int k = tid; k < ncol; k += NT) sB1[k] = a.base1[r1lo + k];
     for (int k = tid; k < ncol * S1; k += NT) sW1[k] = a.W1[(int64_t)r1lo * S1 + k];
-    for (int k = ct; k < i2hi - i2lo; k += TPG) sB2[g * a.F2MAX + k] = a.base2[i2lo + k];
-    for (int k = ct; k < (i2hi - i2lo) * S2; k += TPG) sW2[(size_t)g * a.F2MAX * S2 + k] = a.W2[(int64_t)i2lo * S2 + k];
+    // dim-2 rows of this group: fold the taps clamped onto dst row 0 / m2-1 into the first / last tap, so that
+    // every staged window lies inside [0, m2) (needs m2 >= S2, checked by the host)
+    for (int k = ct; k < nrow_pad; k += TPG) {
+        int *bo = sB2 + g * R2 + k;
+        T *wo = sW2 + ((size_t)g * R2 + k) * S2;
+        if (k < nrow) {
+            const int b = a.base2[i2lo + k];
+            const int bc = min(max(b, 0), a.m2 - S2);
+            T w[S2];
+#pragma unroll
+            for (int s = 0; s < S2; ++s) w[s] = (T)0;
+#pragma unroll
+            for (int s = 0; s < S2; ++s) {
+                const int j = min(max(b + s, 0), a.m2 - 1) - bc;   // tap s lands in slot j of the shifted window
+                const T ws = a.alpha * a.W2[(int64_t)(i2lo + k) * S2 + s];
+#pragma unroll
+                for (int jj = 0; jj < S2; ++jj)
+                    if (jj == j) w[jj] += ws;
+            }
+            *bo = bc;
+#pragma unroll
+            for (int s = 0; s < S2; ++s) wo[s] = w[s];
+        } else {   // padding rows: contribute nothing, do not advance the window
+            *bo = INT_MIN;
+#pragma unroll
+            for (int s = 0; s < S2; ++s) wo[s] = (T)0;
+        }
+    }
     __syncthreads();
 
     // ---- phase 1
@@ -290,47 +359,37 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1)
         const int colA = r1lo + cA;
         const bool haveA = cA < ncol, haveB = cA + 1 < ncol && colA + 1 < a.n1;
         const bool vec = a.vec_ok && haveB;
-        T *tA = sT + (ka - d0) * PH + ct;   // plane 0 (even staged columns), plane 1 at +PLANE
-        auto load = [&](int i2) {
+        T *tp = sT + (ka - d0) * PH + ct;   // next owned row to store; plane 0 (even staged columns), plane 1 at +PLANE
+        const T *lp = src + (int64_t)i2lo * a.n1 + colA;   // next row to load
+        int left = haveA ? nrow : 0;                        // rows still to be loaded
+        auto load = [&]() {
             Pack<T, 2> y;
             y.v[0] = y.v[1] = (T)0;
-            if (haveA && i2 < i2hi) {
-                const T *p = src + (int64_t)i2 * a.n1 + colA;
+            if (left > 0) {
                 if (vec) {
-                    y = ld_pack<T, 2>(p);
+                    y = ld_pack<T, 2>(lp);
                 } else {
-                    y.v[0] = p[0];
-                    if (haveB) y.v[1] = p[1];
+                    y.v[0] = lp[0];
+                    if (haveB) y.v[1] = lp[1];
                 }
             }
+            --left;
+            lp += a.n1;
             return y;
         };
         Pack<T, 2> q[PF];
 #pragma unroll
-        for (int u = 0; u < PF; ++u) q[u] = load(i2lo + u);
+        for (int u = 0; u < PF; ++u) q[u] = load();
         T A0[S2], A1[S2];
 #pragma unroll
         for (int s = 0; s < S2; ++s) A0[s] = A1[s] = (T)0;
         int cur = ka - (S2 - 1);   // dst row of accumulator slot 0
-        int done = 0;              // owned rows already stored
         // retire accumulator slot 0 (dst row `cur`), then shift
         auto retire = [&]() {
-            if (cur < 0) {   // clamped taps: everything below row 0 belongs to row 0
-                if constexpr (S2 > 1) {
-                    A0[1] += A0[0];
-                    A1[1] += A1[0];
-                }
-            } else if (cur >= ka) {
-                if (cur == a.m2 - 1) {   // ... and everything above the last row to the last row
-#pragma unroll
-                    for (int s = 1; s < S2; ++s) {
-                        A0[0] += A0[s];
-                        A1[0] += A1[s];
-                    }
-                }
-                tA[done * PH] = A0[0];
-                tA[done * PH + PLANE] = A1[0];
-                ++done;
+            if (cur >= ka) {
+                tp[0] = A0[0];
+                tp[PLANE] = A1[0];
+                tp += PH;
             }
 #pragma unroll
             for (int s = 0; s + 1 < S2; ++s) {
@@ -340,27 +399,21 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1)
             A0[S2 - 1] = A1[S2 - 1] = (T)0;
             ++cur;
         };
-        const int *gb2 = sB2 + g * a.F2MAX;
-        const T *gw2 = sW2 + (size_t)g * a.F2MAX * S2;
-        for (int i2 = i2lo; i2 < i2hi; i2 += PF) {
+        const int *bq = sB2 + g * R2;
+        const T *wq = sW2 + (size_t)g * R2 * S2;
+        for (int k = 0; k < nrow_pad; k += PF) {
 #pragma unroll
             for (int u = 0; u < PF; ++u) {
-                const int ii = i2 + u;
-                if (ii < i2hi) {
-                    Pack<T, 2> y = q[u];
-                    q[u] = load(ii + PF);
-                    const int b = gb2[ii - i2lo];
-                    while (cur < b && cur < kb) retire();
-                    if (a.alpha != (T)1) {
-                        y.v[0] *= a.alpha;
-                        y.v[1] *= a.alpha;
-                    }
+                const Pack<T, 2> y = q[u];
+                q[u] = load();
+                const int b = bq[k + u];
+                while (cur < b) retire();
+                T w[S2];
+                ld_weights<T, S2>(wq + (k + u) * S2, w);
 #pragma unroll
-                    for (int s = 0; s < S2; ++s) {
-                        const T w = gw2[(ii - i2lo) * S2 + s];
-                        A0[s] = fmaT(w, y.v[0], A0[s]);
-                        A1[s] = fmaT(w, y.v[1], A1[s]);
-                    }
+                for (int s = 0; s < S2; ++s) {
+                    A0[s] = fmaT(w[s], y.v[0], A0[s]);
+                    A1[s] = fmaT(w[s], y.v[1], A1[s]);
                 }
             }
         }
@@ -368,49 +421,56 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1)
     }
     __syncthreads();
 
-    // ---- phase 2: gather along dim 1; NT threads = (NT/128) row slices x 128 dst columns
+    // ---- phase 2: gather along dim 1; NT threads = NSL row slices x CT dst columns
     {
-        constexpr int CT = 128;
-        constexpr int NSL = NT / CT;
+        constexpr int CT = 128, NSL = NT / CT, RS = TD2 / NSL;   // RS rows per slice
         const int kc = tid % CT, sl = tid / CT;
-        for (int kk = kc; kk < c1 - c0; kk += CT) {
+        const int nr = min(RS, d1 - d0 - sl * RS);               // valid rows of this slice
+        for (int kk = kc; kk < c1 - c0 && nr > 0; kk += CT) {
             const int k1 = c0 + kk;
             const int e0 = a.bp1[k1] - r1lo, e1 = a.bp1[k1 + S1] - r1lo;   // contributing staged src columns
-            // interior columns: one tap per src column, in registers (static indexing); edge columns (clamped
-            // taps, several per src column) and very long lists go through the slow loop
-            int off[ADJ_MAXE];
-            T w[ADJ_MAXE];
+            const T *rowbase = sT + sl * RS * PH;
+            T *d = dst + (int64_t)(d0 + sl * RS) * a.m1 + k1;
+            T acc[RS];
+#pragma unroll
+            for (int r = 0; r < RS; ++r) acc[r] = (T)0;
+            // interior columns: one tap per src column (static register indexing); edge columns carry the
+            // clamped taps of every out-of-range src column and take the generic loop, as do very long lists
             const bool interior = k1 > 0 && k1 < a.m1 - 1;
             const int cnt = interior ? min(e1 - e0, ADJ_MAXE) : 0;
 #pragma unroll
             for (int k = 0; k < ADJ_MAXE; ++k) {
-                off[k] = 0;
-                w[k] = (T)0;
                 if (k < cnt) {
                     const int c = e0 + k;
-                    off[k] = (c & 1) * PLANE + (c >> 1);
-                    w[k] = sW1[c * S1 + (k1 - sB1[c])];
+                    const T wk = sW1[c * S1 + (k1 - sB1[c])];
+                    const T *p = rowbase + (c & 1) * PLANE + (c >> 1);
+#pragma unroll
+                    for (int r = 0; r < RS; ++r) acc[r] = fmaT(wk, p[r * PH], acc[r]);
                 }
             }
-            const int e_reg_end = e0 + cnt;
-            for (int r = sl; r < d1 - d0; r += NSL) {
-                const T *row = sT + r * PH;
-                T acc = (T)0;
+            for (int e = e0 + cnt; e < e1; ++e) {
+                const int b = sB1[e];
+                int slo = k1 - b, shi = k1 - b;   // taps s with clamp(b + s) == k1
+                if (k1 == 0) slo = 0;
+                if (k1 == a.m1 - 1) shi = S1 - 1;
+                slo = max(slo, 0);
+                shi = min(shi, S1 - 1);
+                const T *p = rowbase + (e & 1) * PLANE + (e >> 1);
+                for (int s = slo; s <= shi; ++s) {
+                    const T ws = sW1[e * S1 + s];
 #pragma unroll
-                for (int k = 0; k < ADJ_MAXE; ++k)
-                    if (k < cnt) acc = fmaT(w[k], row[off[k]], acc);
-                for (int e = e_reg_end; e < e1; ++e) {
-                    const int b = sB1[e];
-                    int slo = k1 - b, shi = k1 - b;   // taps s with clamp(b + s) == k1
-                    if (k1 == 0) slo = 0;
-                    if (k1 == a.m1 - 1) shi = S1 - 1;
-                    slo = max(slo, 0);
-                    shi = min(shi, S1 - 1);
-                    const T t = row[(e & 1) * PLANE + (e >> 1)];
-                    for (int s = slo; s <= shi; ++s) acc = fmaT(sW1[e * S1 + s], t, acc);
+                    for (int r = 0; r < RS; ++r) acc[r] = fmaT(ws, p[r * PH], acc[r]);
                 }
-                T *d = dst + (int64_t)(d0 + r) * a.m1 + k1;
-                *d = a.beta == (T)0 ? acc : fmaT(a.beta, *d, acc);
+            }
+#pragma unroll
+            for (int r = 0; r < RS; ++r) {
+                if (r < nr) {
+                    T *dr = d + (int64_t)r * a.m1;
+                    if constexpr (BETA)
+                        *dr = fmaT(a.beta, *dr, acc[r]);
+                    else
+                        *dr = acc[r];
+                }
             }
         }
     }
@@ -435,24 +495,28 @@ static int launch_fwd(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     int rc = table_fwd_span(t1, TO1, st, &span1);
     if (rc == LI_OK) rc = table_fwd_span(t2, FWD_TO2, st, &span2);
     if (rc != LI_OK) return rc;
-    a.F1MAX = span1 + S1, a.F2MAX = span2 + S2;
+    // staged pitch: footprint + 1 spare tap (paired load) + up to 3 columns of alignment shift, multiple of 4
+    a.F1MAX = (span1 + S1 + 1 + 3 + 3) & ~3;
+    a.F2MAX = span2 + S2 + S2;   // + S2 padding rows (the row loop is unrolled by S2)
     a.tiles1 = (a.n1 + TO1 - 1) / TO1, a.tiles2 = (a.n2 + FWD_TO2 - 1) / FWD_TO2;
-    const size_t smem = ((size_t)a.F2MAX * (a.F1MAX + 1) + FWD_TO2 * S2) * sizeof(T) +
+    // 16-byte staging loads need aligned source rows; 8-byte stores need aligned destination rows
+    a.vec_ok = (a.m1 % 4 == 0) && (((uintptr_t)a.src) % 16 == 0) && (a.n1 % 2 == 0) &&
+               (((uintptr_t)a.dst) % (2 * sizeof(T)) == 0) && a.F1MAX <= 256;
+    const size_t smem = ((size_t)a.F2MAX * a.F1MAX + FWD_TO2 * S2) * sizeof(T) +
                         (FWD_TO2 + (size_t)NG * a.F2MAX) * sizeof(int);
     if (smem > (size_t)kSmemLimit) return LI_OK;   // footprint too large for staging: decline
     const int64_t blocks = (int64_t)a.tiles1 * a.tiles2 * nbatch;
     LI_REQUIRE(blocks <= 0x7fffffffLL, LI_ERR_UNSUPPORTED, "too many tiles");
-    if (t1->max_step <= 1) {
-        auto kern = sep2d_fwd_kernel<T, S1, S2, NG, true>;
-        rc = set_smem(kern, smem);
-        if (rc != LI_OK) return rc;
-        kern<<<(unsigned)blocks, FWD_NT, smem, st>>>(a);
-    } else {
-        auto kern = sep2d_fwd_kernel<T, S1, S2, NG, false>;
-        rc = set_smem(kern, smem);
-        if (rc != LI_OK) return rc;
-        kern<<<(unsigned)blocks, FWD_NT, smem, st>>>(a);
+    const bool pair = t1->max_step <= 1, beta = a.beta != (T)0;
+#define LI_FWD(P, B)                                                          \
+    if (pair == P && beta == B) {                                             \
+        auto kern = sep2d_fwd_kernel<T, S1, S2, NG, P, B>;                    \
+        rc = set_smem(kern, smem);                                            \
+        if (rc != LI_OK) return rc;                                           \
+        kern<<<(unsigned)blocks, FWD_NT, smem, st>>>(a);                      \
     }
+    LI_FWD(true, false) LI_FWD(true, true) LI_FWD(false, false) LI_FWD(false, true)
+#undef LI_FWD
     LI_CHECK_LAUNCH();
     *done = true;
     return LI_OK;
@@ -463,6 +527,7 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
                       bool *done)
 {
     constexpr int NG = 2, PT = 2 * (ADJ_NT / NG), RG = ADJ_TD2 / NG;
+    if (a.m2 < S2 || a.m1 < 2) return LI_OK;   // decline: the edge folding needs a full window inside the array
     int rc = table_ensure_rowstart(t1, st);
     if (rc == LI_OK) rc = table_ensure_rowstart(t2, st);
     if (rc != LI_OK) return rc;
@@ -483,17 +548,25 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     int r2 = 0;
     rc = table_adj_rows(t2, RG, st, &r2);
     if (rc != LI_OK) return rc;
-    a.F2MAX = r2;
+    a.F2MAX = (r2 + ADJ_PF - 1) / ADJ_PF * ADJ_PF;
     a.tiles1 = (a.m1 + TD1 - 1) / TD1, a.tiles2 = (a.m2 + ADJ_TD2 - 1) / ADJ_TD2;
+    a.vec_ok = (a.n1 % 2 == 0) && (((uintptr_t)a.src) % (2 * sizeof(T)) == 0);
     const size_t smem = (2 * ((size_t)ADJ_TD2 * (PT / 2) + 16) + (size_t)PT * S1 + (size_t)NG * a.F2MAX * S2) * sizeof(T) +
                         ((size_t)PT + (size_t)NG * a.F2MAX) * sizeof(int);
     if (smem > (size_t)kSmemLimit) return LI_OK;
     const int64_t blocks = (int64_t)a.tiles1 * a.tiles2 * nbatch;
     LI_REQUIRE(blocks <= 0x7fffffffLL, LI_ERR_UNSUPPORTED, "too many tiles");
-    auto kern = sep2d_adj_kernel<T, S1, S2, NG>;
-    rc = set_smem(kern, smem);
-    if (rc != LI_OK) return rc;
-    kern<<<(unsigned)blocks, ADJ_NT, smem, st>>>(a, TD1);
+    if (a.beta != (T)0) {
+        auto kern = sep2d_adj_kernel<T, S1, S2, NG, true>;
+        rc = set_smem(kern, smem);
+        if (rc != LI_OK) return rc;
+        kern<<<(unsigned)blocks, ADJ_NT, smem, st>>>(a, TD1);
+    } else {
+        auto kern = sep2d_adj_kernel<T, S1, S2, NG, false>;
+        rc = set_smem(kern, smem);
+        if (rc != LI_OK) return rc;
+        kern<<<(unsigned)blocks, ADJ_NT, smem, st>>>(a, TD1);
+    }
     LI_CHECK_LAUNCH();
     *done = true;
     return LI_OK;
@@ -510,16 +583,12 @@ static int fused_T(int adjoint, const li_table *t1, const li_table *t2, int64_t 
     a.n1 = (int)t1->nrows, a.n2 = (int)t2->nrows, a.m1 = (int)t1->ncols, a.m2 = (int)t2->ncols;
     a.alpha = (T)alpha, a.beta = (T)beta;
     a.src = (const T *)src, a.dst = (T *)dst;
-    // the big ("rows"-side) array is accessed with 2-element vectors when its rows are aligned
-    const void *big = adjoint ? src : (const void *)dst;
-    a.vec_ok = (a.n1 % 2 == 0) && (((uintptr_t)big) % (2 * sizeof(T)) == 0);
     const int S1 = t1->S, S2 = t2->S;
 #define LI_SEP(A1, A2)                                                                   \
     if (S1 == A1 && S2 == A2)                                                            \
         return adjoint ? launch_adj<T, A1, A2>(a, t1, t2, nbatch, st, done)             \
                        : launch_fwd<T, A1, A2>(a, t1, t2, nbatch, st, done);
-    LI_SEP(1, 1) LI_SEP(2, 2) LI_SEP(3, 3) LI_SEP(4, 4) LI_SEP(6, 6) LI_SEP(8, 8)
-    LI_SEP(2, 4) LI_SEP(4, 2) LI_SEP(4, 6) LI_SEP(6, 4)
+    LI_SEP(2, 2) LI_SEP(4, 4) LI_SEP(6, 6) LI_SEP(2, 4) LI_SEP(4, 2) LI_SEP(4, 6) LI_SEP(6, 4)
 #undef LI_SEP
     return LI_OK;   // size pair not built: decline
 }
