@@ -87,15 +87,60 @@ struct SepArgs {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Forward: a register pipeline.  A thread owns two adjacent output columns (i1, i1+1) of a tile of
-// TO1 = 2*TPG columns x TO2 rows; NG row groups split the TO2 rows.  For every source row of its group, in
-// ascending order, the thread interpolates along dim 1 from the staged tile (taps and weights in
-// registers; the two columns share their loads when the table never advances by more than one column
-// per row, i.e. for any up-sampling), pushes the value into a window of S2 registers whose rotation is
-// static (the loop is unrolled by S2), and emits every output row whose dim-2 window has just become
-// complete (block-uniform count).  The dim-1 result never touches shared memory.
-constexpr int FWD_TO2 = 64;
+// Forward: a streaming register pipeline.
+//
+// A CTA owns a strip of TO1 = 2*NT output columns and a chunk of output rows; a thread owns two adjacent
+// output columns (i1, i1+1).  The source rows the chunk needs are streamed, in ascending order, through a
+// ring of shared-memory stages filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP)
+// issued by one thread NSTAGE-1 stages ahead.  For every source row the thread
+//   1. interpolates along dim 1 from the staged row (taps and weights in registers; the two columns share
+//      their loads whenever the table never advances by more than one column per row, i.e. any up-sampling),
+//   2. pushes the value into a window of S2 registers whose rotation is static (the row loop is unrolled by
+//      a multiple of S2),
+//   3. emits every output row whose dim-2 window has just become complete (block-uniform count).
+// The dim-1 result never touches shared memory, no source row is re-computed, and src/dst cross HBM once.
+// Flat/SafeFlat clamping is applied while staging (clamped row index for the copy, replicated edge columns).
 constexpr int FWD_NT = 256;
+constexpr int FWD_NSTAGE = 3;
+constexpr int FWD_MAXCR = 256;   // output rows per chunk (one thread per row when counting completions)
+
+template <int S2>
+struct FwdK {   // source rows per stage: a multiple of S2 (static window rotation)
+    static constexpr int value = S2 >= 4 ? S2 : (S2 == 3 ? 6 : 4);
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes: multiple of 16, both sides 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 template <typename T, int S>
 __device__ __forceinline__ void ld_weights(const T *p, T (&w)[S])
@@ -115,72 +160,81 @@ __device__ __forceinline__ void ld_weights(const T *p, T (&w)[S])
     }
 }
 
-template <typename T, int S1, int S2, int NG, bool PAIR, bool BETA>
+template <typename T, int S1, int S2, bool PAIR, bool BETA>
 __global__ void __launch_bounds__(FWD_NT, (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : 2)
-sep2d_fwd_kernel(const SepArgs<T> a)
+sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, const int NCNT /* staged-row counters */)
 {
-    constexpr int NT = FWD_NT, TPG = NT / NG, TO1 = 2 * TPG, TO2 = FWD_TO2, RG = TO2 / NG;
-    static_assert(NG * RG == TO2 && TO2 <= NT, "bad tiling");
+    constexpr int NT = FWD_NT, TO1 = 2 * NT, K = FwdK<S2>::value, NSTAGE = FWD_NSTAGE;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int P1 = a.F1MAX;                              // row pitch of the staged tile (multiple of 4, >= footprint + 4)
-    const int R2 = a.F2MAX;                              // staged rows incl. S2 rows of padding
-    T *sS = reinterpret_cast<T *>(smem_raw);             // [R2][P1] staged src tile
-    T *sW2 = sS + (size_t)R2 * P1;                       // [TO2][S2]  alpha * W2
-    int *sB2 = reinterpret_cast<int *>(sW2 + TO2 * S2);  // [TO2]
-    int *sCnt = sB2 + TO2;                               // [NG][R2] outputs completed by each source row
+    const int P1 = a.F1MAX;                                  // elements per staged row (multiple of 4)
+    T *sS = reinterpret_cast<T *>(smem_raw);                 // [NSTAGE][K][P1] ring of source rows
+    T *sW2 = sS + (size_t)NSTAGE * K * P1;                   // [CR][S2]  alpha * W2
+    int *sCnt = reinterpret_cast<int *>(sW2 + (size_t)CR * S2);   // [NCNT] outputs completed by each source row
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sCnt + ((NCNT + 1) & ~1));   // [NSTAGE]
 
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
-    const int tile1 = bid % a.tiles1;
+    const int strip = bid % a.tiles1;
     bid /= a.tiles1;
-    const int tile2 = bid % a.tiles2;
+    const int chunk = bid % a.tiles2;
     const int64_t batch = bid / a.tiles2;
-    const int i1_0 = tile1 * TO1, i2_0 = tile2 * TO2;
+    const int i1_0 = strip * TO1;
+    const int i2a = chunk * CR, rows = min(CR, a.n2 - i2a);   // output rows [i2a, i2a + rows)
     const T *src = a.src + batch * (int64_t)a.m1 * a.m2;
     T *dst = a.dst + batch * (int64_t)a.n1 * a.n2;
 
-    // footprint of the tile (tables are monotone): [lo, lo + F) in each dimension
+    // footprint (tables are monotone): staged column c <-> source column lo1a + c, staged row r <-> lo2 + r
     const int lo1 = a.base1[i1_0], F1 = a.base1[min(i1_0 + TO1, a.n1) - 1] + S1 - lo1;
-    const int rows = min(TO2, a.n2 - i2_0);
-    const int lo2 = a.base2[i2_0], F2 = a.base2[i2_0 + rows - 1] + S2 - lo2;
+    const int lo1a = a.vec_ok ? (lo1 & ~3) : lo1;
+    const int lo2 = a.base2[i2a];
+    const int NR = a.base2[i2a + rows - 1] + S2 - lo2;        // source rows needed
+    const int NJ = (NR + K - 1) / K;                         // stages
+    // columns of the staged row that exist in the source; the rest are replicated edge columns
+    const int cv0 = max(0, -lo1a), cv1 = min(P1, a.m1 - lo1a);
+    const bool bulk = a.vec_ok;                              // TMA bulk copies need 16-byte aligned row segments
+    const bool patch = cv0 > 0 || cv1 < F1 + (lo1 - lo1a) + 1;
 
-    for (int k = tid; k < NG * R2; k += NT) sCnt[k] = 0;
+    for (int k = tid; k < NCNT; k += NT) sCnt[k] = 0;
+    if (tid == 0) {
+#pragma unroll
+        for (int sgi = 0; sgi < NSTAGE; ++sgi) mbar_init(&bar[sgi], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    if (tid < rows) {
-        const int b = a.base2[i2_0 + tid];
-        sB2[tid] = b;
-        atomicAdd(&sCnt[(tid / RG) * R2 + (b - lo2 + S2 - 1)], 1);
-    }
-    for (int k = tid; k < rows * S2; k += NT) sW2[k] = a.alpha * a.W2[(int64_t)i2_0 * S2 + k];
 
-    // stage the source tile; column c of the staged tile <-> source column lo1a + c
-    const int lo1a = a.vec_ok ? (lo1 & ~3) : lo1;   // vec_ok: m1 % 4 == 0 and src is 16-byte aligned
-    const int shift1 = lo1 - lo1a;
-    const bool interior = a.vec_ok && lo1a >= 0 && lo1a + P1 <= a.m1 && lo2 >= 0 && lo2 + F2 <= a.m2;
-    if (interior) {
-        // 64 x 4 thread grid: 16-byte loads, no clamping
-        const int cx = tid & 63, ry = tid >> 6;
-        if (cx * 4 < F1 + shift1) {
-            const T *g = src + (int64_t)(lo2 + ry) * a.m1 + lo1a + cx * 4;
-            T *sp = sS + ry * P1 + cx * 4;
-            for (int r = ry; r < F2; r += NT / 64) {
-                st_pack<T, 4>(sp, ld_pack<T, 4>(g));
-                g += (int64_t)(NT / 64) * a.m1;
-                sp += (NT / 64) * P1;
-            }
+    auto issue = [&](int j) {   // producer (one thread): stage j <- source rows lo2 + j*K .. + K-1, clamped
+        uint64_t *b = &bar[j % NSTAGE];
+        T *buf = sS + (size_t)(j % NSTAGE) * K * P1;
+        const uint32_t bytes = (uint32_t)((cv1 - cv0) * sizeof(T));
+        mbar_expect_tx(b, bytes * K);
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+            const int row = clampi(lo2 + j * K + r, a.m2 - 1);
+            bulk_g2s(buf + r * P1 + cv0, src + (int64_t)row * a.m1 + lo1a + cv0, bytes, b);
         }
+    };
+    auto stage_manual = [&](int j) {   // unaligned sources: plain loads by every thread
+        T *buf = sS + (size_t)(j % NSTAGE) * K * P1;
+        for (int idx = tid; idx < K * P1; idx += NT) {
+            const int r = idx / P1, c = idx - r * P1;
+            const int row = clampi(lo2 + j * K + r, a.m2 - 1);
+            buf[idx] = src[(int64_t)row * a.m1 + clampi(lo1a + c, a.m1 - 1)];
+        }
+    };
+    if (bulk) {
+        if (tid == 0)
+            for (int j = 0; j < NSTAGE - 1 && j < NJ; ++j) issue(j);
     } else {
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int r = warp; r < F2; r += NT / 32) {
-            const T *row = src + (int64_t)clampi(lo2 + r, a.m2 - 1) * a.m1;
-            for (int c = lane; c < F1 + shift1; c += 32) sS[r * P1 + c] = row[clampi(lo1a + c, a.m1 - 1)];
-        }
+        for (int j = 0; j < NSTAGE - 1 && j < NJ; ++j) stage_manual(j);
     }
+
+    // completion counters and dim-2 weights of the chunk
+    for (int k = tid; k < rows; k += NT) atomicAdd(&sCnt[a.base2[i2a + k] - lo2 + S2 - 1], 1);
+    for (int k = tid; k < rows * S2; k += NT) sW2[k] = a.alpha * a.W2[(int64_t)i2a * S2 + k];
 
     // per-thread dim-1 taps
-    const int g = tid / TPG, cA = 2 * (tid % TPG);
-    const int colA = i1_0 + cA;
+    const int colA = i1_0 + 2 * tid;
     const bool haveA = colA < a.n1, haveB = colA + 1 < a.n1;
     const int iA = min(colA, a.n1 - 1), iB = min(colA + 1, a.n1 - 1);
     const int offA = a.base1[iA] - lo1a, offB = a.base1[iB] - lo1a;
@@ -191,30 +245,38 @@ sep2d_fwd_kernel(const SepArgs<T> a)
         w1B[s] = a.W1[(int64_t)iB * S1 + s];
     }
     const bool shift = offB != offA;   // PAIR: offB - offA is 0 or 1
-    __syncthreads();
-
-    const int r0 = g * RG;
-    if (!haveA || r0 >= rows) return;
-    const int r1 = min(r0 + RG, rows);
-    const int rb = sB2[r0] - lo2, re = sB2[r1 - 1] - lo2 + S2;   // source rows of this group
-    const bool vec = a.vec_ok && haveB;                         // (n1 is even whenever vec_ok)
-    const T *wp = sW2 + r0 * S2;                                // weights of the next output row
-    T *dp = dst + (int64_t)(i2_0 + r0) * a.n1 + colA;           // next output element
-    const int *cp = sCnt + g * R2;
-    const T *pA = sS + offA, *pB = sS + offB;
+    const bool vec = a.vec_ok && haveB;
+    const T *wp = sW2;                                  // weights of the next output row
+    T *dp = dst + (int64_t)i2a * a.n1 + colA;           // next output element
     T hA[S2], hB[S2];
 #pragma unroll
     for (int s = 0; s < S2; ++s) hA[s] = hB[s] = (T)0;
 
-    // rows [re, rb + ceil((re-rb)/S2)*S2) are padding: they exist in smem, complete no output
-    for (int r = rb; r < re; r += S2) {
+    for (int j = 0; j < NJ; ++j) {
+        __syncthreads();   // every thread is done with stage j-1: its buffer may be refilled
+        if (bulk) {
+            if (tid == 0 && j + NSTAGE - 1 < NJ) issue(j + NSTAGE - 1);
+            mbar_wait(&bar[j % NSTAGE], (uint32_t)((j / NSTAGE) & 1));
+        } else if (j + NSTAGE - 1 < NJ) {
+            stage_manual(j + NSTAGE - 1);   // (visible after the next barrier; stage j was written two barriers ago)
+        }
+        T *buf = sS + (size_t)(j % NSTAGE) * K * P1;
+        if (bulk && patch) {   // replicate the first / last source column into the out-of-range staged columns
+            for (int idx = tid; idx < K * P1; idx += NT) {
+                const int r = idx / P1, c = idx - r * P1;
+                if (c < cv0) buf[idx] = buf[r * P1 + cv0];
+                if (c >= cv1) buf[idx] = buf[r * P1 + cv1 - 1];
+            }
+            __syncthreads();
+        }
+        if (!haveA) continue;
+        const int *cp = sCnt + j * K;
 #pragma unroll
-        for (int u = 0; u < S2; ++u) {
-            const int rr = r + u;
-            // pass 1: dim 1, from the staged tile
+        for (int u = 0; u < K; ++u) {
+            // pass 1: dim 1, from the staged row
             T accA, accB;
             if constexpr (PAIR) {
-                const T *p = pA + rr * P1;
+                const T *p = buf + u * P1 + offA;
                 T v[S1 + 1];
 #pragma unroll
                 for (int s = 0; s <= S1; ++s) v[s] = p[s];
@@ -226,7 +288,7 @@ sep2d_fwd_kernel(const SepArgs<T> a)
                     accB = fmaT(shift ? v[s + 1] : v[s], w1B[s], accB);
                 }
             } else {
-                const T *p = pA + rr * P1, *q = pB + rr * P1;
+                const T *p = buf + u * P1 + offA, *q = buf + u * P1 + offB;
                 accA = p[0] * w1A[0];
                 accB = q[0] * w1B[0];
 #pragma unroll
@@ -235,10 +297,10 @@ sep2d_fwd_kernel(const SepArgs<T> a)
                     accB = fmaT(q[s], w1B[s], accB);
                 }
             }
-            hA[u] = accA;
-            hB[u] = accB;
-            // pass 2: emit the output rows whose window [rr-S2+1, rr] is now complete
-            for (int n = cp[rr]; n > 0; --n) {
+            hA[u % S2] = accA;
+            hB[u % S2] = accB;
+            // pass 2: emit the output rows whose window [row-S2+1, row] is now complete
+            for (int n = cp[u]; n > 0; --n) {
                 T w2[S2];
                 ld_weights<T, S2>(wp, w2);
                 wp += S2;
@@ -486,34 +548,51 @@ static int set_smem(KernT kern, size_t smem)
     return LI_OK;
 }
 
+static int num_sms()
+{
+    static thread_local int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
 template <typename T, int S1, int S2>
 static int launch_fwd(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64_t nbatch, cudaStream_t st,
                       bool *done)
 {
-    constexpr int NG = 2, TO1 = 2 * (FWD_NT / NG);
+    constexpr int TO1 = 2 * FWD_NT, K = FwdK<S2>::value;
+    a.tiles1 = (a.n1 + TO1 - 1) / TO1;
+    // chunks of output rows: about one wave of 4 CTAs per SM, chunk length a multiple of 8 and at most FWD_MAXCR
+    const int64_t target = (int64_t)num_sms() * 4;
+    int chunks = (int)std::max<int64_t>(1, (target + a.tiles1 * nbatch - 1) / (a.tiles1 * nbatch));
+    int CR = (a.n2 + chunks - 1) / chunks;
+    CR = std::min(FWD_MAXCR, std::max(8, (CR + 7) & ~7));
+    a.tiles2 = (a.n2 + CR - 1) / CR;
     int span1 = 0, span2 = 0;
     int rc = table_fwd_span(t1, TO1, st, &span1);
-    if (rc == LI_OK) rc = table_fwd_span(t2, FWD_TO2, st, &span2);
+    if (rc == LI_OK) rc = table_fwd_span(t2, CR, st, &span2);
     if (rc != LI_OK) return rc;
-    // staged pitch: footprint + 1 spare tap (paired load) + up to 3 columns of alignment shift, multiple of 4
+    // staged row: footprint + 1 spare tap (paired load) + up to 3 columns of alignment shift, multiple of 4
     a.F1MAX = (span1 + S1 + 1 + 3 + 3) & ~3;
-    a.F2MAX = span2 + S2 + S2;   // + S2 padding rows (the row loop is unrolled by S2)
-    a.tiles1 = (a.n1 + TO1 - 1) / TO1, a.tiles2 = (a.n2 + FWD_TO2 - 1) / FWD_TO2;
-    // 16-byte staging loads need aligned source rows; 8-byte stores need aligned destination rows
+    const int NCNT = (span2 + S2 + K - 1) / K * K;   // staged source rows of a chunk, padded to whole stages
+    // 16-byte bulk copies need aligned source rows; 8-byte stores need aligned destination rows
     a.vec_ok = (a.m1 % 4 == 0) && (((uintptr_t)a.src) % 16 == 0) && (a.n1 % 2 == 0) &&
-               (((uintptr_t)a.dst) % (2 * sizeof(T)) == 0) && a.F1MAX <= 256;
-    const size_t smem = ((size_t)a.F2MAX * a.F1MAX + FWD_TO2 * S2) * sizeof(T) +
-                        (FWD_TO2 + (size_t)NG * a.F2MAX) * sizeof(int);
+               (((uintptr_t)a.dst) % (2 * sizeof(T)) == 0);
+    const size_t smem = ((size_t)FWD_NSTAGE * K * a.F1MAX + (size_t)CR * S2) * sizeof(T) +
+                        (size_t)((NCNT + 1) & ~1) * sizeof(int) + FWD_NSTAGE * sizeof(uint64_t);
     if (smem > (size_t)kSmemLimit) return LI_OK;   // footprint too large for staging: decline
     const int64_t blocks = (int64_t)a.tiles1 * a.tiles2 * nbatch;
     LI_REQUIRE(blocks <= 0x7fffffffLL, LI_ERR_UNSUPPORTED, "too many tiles");
     const bool pair = t1->max_step <= 1, beta = a.beta != (T)0;
 #define LI_FWD(P, B)                                                          \
     if (pair == P && beta == B) {                                             \
-        auto kern = sep2d_fwd_kernel<T, S1, S2, NG, P, B>;                    \
+        auto kern = sep2d_fwd_kernel<T, S1, S2, P, B>;                        \
         rc = set_smem(kern, smem);                                            \
         if (rc != LI_OK) return rc;                                           \
-        kern<<<(unsigned)blocks, FWD_NT, smem, st>>>(a);                      \
+        kern<<<(unsigned)blocks, FWD_NT, smem, st>>>(a, CR, NCNT);            \
     }
     LI_FWD(true, false) LI_FWD(true, true) LI_FWD(false, false) LI_FWD(false, true)
 #undef LI_FWD
