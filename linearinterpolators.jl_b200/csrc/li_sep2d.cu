@@ -106,7 +106,7 @@ constexpr int FWD_MAXCR = 256;   // output rows per chunk (one thread per row wh
 
 template <int S2>
 struct FwdK {   // source rows per stage: a multiple of S2 (static window rotation)
-    static constexpr int value = S2 >= 4 ? S2 : (S2 == 3 ? 6 : 4);
+    static constexpr int value = S2 == 4 ? 8 : (S2 > 4 ? S2 : (S2 == 3 ? 6 : 8));
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -193,7 +193,8 @@ sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, c
     // columns of the staged row that exist in the source; the rest are replicated edge columns
     const int cv0 = max(0, -lo1a), cv1 = min(P1, a.m1 - lo1a);
     const bool bulk = a.vec_ok;                              // TMA bulk copies need 16-byte aligned row segments
-    const bool patch = cv0 > 0 || cv1 < F1 + (lo1 - lo1a) + 1;
+    const int need1 = min(P1, F1 + (lo1 - lo1a) + 1);        // staged columns actually read (incl. the spare tap)
+    const bool patch = cv0 > 0 || cv1 < need1;
 
     for (int k = tid; k < NCNT; k += NT) sCnt[k] = 0;
     if (tid == 0) {
@@ -262,44 +263,51 @@ sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, c
         }
         T *buf = sS + (size_t)(j % NSTAGE) * K * P1;
         if (bulk && patch) {   // replicate the first / last source column into the out-of-range staged columns
-            for (int idx = tid; idx < K * P1; idx += NT) {
-                const int r = idx / P1, c = idx - r * P1;
-                if (c < cv0) buf[idx] = buf[r * P1 + cv0];
-                if (c >= cv1) buf[idx] = buf[r * P1 + cv1 - 1];
+            const int warp = tid >> 5, lane = tid & 31;   // warp <-> staged row, lane <-> column to patch
+            if (warp < K) {
+                T *row = buf + warp * P1;
+                if (lane < cv0) row[lane] = row[cv0];
+                for (int c = cv1 + lane; c < need1; c += 32) row[c] = row[cv1 - 1];
             }
             __syncthreads();
         }
         if (!haveA) continue;
         const int *cp = sCnt + j * K;
+        // pass 1: dim 1, for the K staged rows at once (independent FMA chains)
+        T nA[K], nB[K];
 #pragma unroll
         for (int u = 0; u < K; ++u) {
-            // pass 1: dim 1, from the staged row
-            T accA, accB;
             if constexpr (PAIR) {
                 const T *p = buf + u * P1 + offA;
                 T v[S1 + 1];
 #pragma unroll
                 for (int s = 0; s <= S1; ++s) v[s] = p[s];
-                accA = v[0] * w1A[0];
-                accB = (shift ? v[1] : v[0]) * w1B[0];
+                T accA = v[0] * w1A[0];
+                T accB = (shift ? v[1] : v[0]) * w1B[0];
 #pragma unroll
                 for (int s = 1; s < S1; ++s) {
                     accA = fmaT(v[s], w1A[s], accA);
                     accB = fmaT(shift ? v[s + 1] : v[s], w1B[s], accB);
                 }
+                nA[u] = accA, nB[u] = accB;
             } else {
                 const T *p = buf + u * P1 + offA, *q = buf + u * P1 + offB;
-                accA = p[0] * w1A[0];
-                accB = q[0] * w1B[0];
+                T accA = p[0] * w1A[0];
+                T accB = q[0] * w1B[0];
 #pragma unroll
                 for (int s = 1; s < S1; ++s) {
                     accA = fmaT(p[s], w1A[s], accA);
                     accB = fmaT(q[s], w1B[s], accB);
                 }
+                nA[u] = accA, nB[u] = accB;
             }
-            hA[u % S2] = accA;
-            hB[u % S2] = accB;
+        }
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            hA[u % S2] = nA[u];
+            hB[u % S2] = nB[u];
             // pass 2: emit the output rows whose window [row-S2+1, row] is now complete
+#pragma unroll 1
             for (int n = cp[u]; n > 0; --n) {
                 T w2[S2];
                 ld_weights<T, S2>(wp, w2);
