@@ -337,37 +337,52 @@ sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Adjoint: the transpose of the above.  The CTA owns the dst tile [c0, c0+TD1) x [d0, d0+TD2) of dst[m1, m2].
-//   phase 1 (dim 2): a thread owns two adjacent src columns and streams the src rows feeding its row
-//            group in ascending order (coalesced vector loads, a register queue PF rows ahead), adding each
-//            row into S2 accumulators -- the order of the reference's sequential scatter.  When the window
-//            base advances, the oldest accumulator is a finished dst row and goes to shared memory.
-//            The clamped taps of the first/last dst rows are folded into the staged copy of the weights, so
-//            the hot loop has no edge cases.
-//   phase 2 (dim 1): a thread owns one dst column; its taps (one per contributing src column) sit in
-//            registers and are reused for every row.  sT is stored in two parity planes so that the
-//            stride-2 gather of a 2x operator is bank-conflict free.
+// Adjoint: the transpose of the forward operator, tile-owned and atomic-free.
+//
+// The CTA owns the dst tile [c0, c0+TD1) x [d0, d0+TD2) of dst[m1, m2]; the big src array is read exactly once
+// per tile (plus halos) straight from global memory, many small CTAs keep every SM busy.
+//   phase 1 (dim 2): a thread owns two adjacent src columns; NG row groups each own RG dst rows.  The src rows
+//            feeding the group arrive through a thread-private ring of cp.async copies (depth D, no barrier, no
+//            register staging), in ascending order.  dst rows are finished one at a time: for dst row v the
+//            thread adds every src row whose window starts at v into S2 accumulators (static slot rotation:
+//            the row loop is unrolled by S2), then slot v is complete -- the order of the reference's
+//            sequential scatter (src/tabulated.jl:455-462) -- and goes to shared memory (sT).  The clamped taps
+//            of the first/last dst rows are folded into the staged copy of the weights (no edge cases).
+//   phase 2 (dim 1): a thread owns one dst column and RS rows; its taps (one per contributing src column) sit
+//            in registers.  sT is stored in two parity planes so that the stride-2 gather of a 2x operator is
+//            bank-conflict free.
+// No atomics: every dst element is written once by its owner, in a fixed order -> deterministic.
 constexpr int ADJ_TD2 = 32;
 constexpr int ADJ_NT = 256;
+constexpr int ADJ_NG = 2;
+constexpr int ADJ_D = 8;      // src rows in flight per thread (cp.async ring depth)
 constexpr int ADJ_MAXE = 12;  // taps per dst column kept in registers; longer lists use a slow loop
-constexpr int ADJ_PF = 4;     // src rows in flight per thread
 
-template <typename T, int S1, int S2, int NG, bool BETA>
-__global__ void __launch_bounds__(ADJ_NT, (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : 2)
-sep2d_adj_kernel(const SepArgs<T> a, const int TD1)
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *dst_smem, const void *src_gmem)
 {
-    constexpr int TD2 = ADJ_TD2, NT = ADJ_NT, TPG = NT / NG, PT = 2 * TPG, RG = TD2 / NG, PF = ADJ_PF;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int S1, int S2, bool BETA>
+__global__ void __launch_bounds__(ADJ_NT, (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : 2)
+sep2d_adj_kernel(const SepArgs<T> a, const int TD1, const int R2 /* staged dim-2 rows per group */)
+{
+    constexpr int TD2 = ADJ_TD2, NT = ADJ_NT, NG = ADJ_NG, TPG = NT / NG, PT = 2 * TPG, RG = TD2 / NG, D = ADJ_D;
     constexpr int PH = PT / 2;               // columns per parity plane
     constexpr int PLANE = TD2 * PH + 16;     // plane stride: +16 banks so that unit-stride gathers do not collide
     static_assert(NG * RG == TD2, "bad tiling");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int R2 = a.F2MAX;                                  // staged src rows per group (multiple of PF)
     T *sT = reinterpret_cast<T *>(smem_raw);                 // [2][TD2][PH] (+skew)
-    T *sW1 = sT + 2 * PLANE;                                 // [PT][S1]
+    T *sRing = sT + 2 * PLANE;                               // [D][NT][2] thread-private ring of src row pairs
+    T *sW1 = sRing + (size_t)D * NT * 2;                     // [PT][S1]
     T *sW2 = sW1 + (size_t)PT * S1;                          // [NG][R2][S2]  alpha * W2, edge taps folded
     int *sB1 = reinterpret_cast<int *>(sW2 + (size_t)NG * R2 * S2);   // [PT]
-    int *sB2 = sB1 + PT;                                     // [NG][R2]
+    int *sNv = sB1 + PT;                                     // [NG][RG + S2] src rows whose (folded) window starts at a dst row
 
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -387,108 +402,105 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1)
 
     const int g = tid / TPG, ct = tid % TPG;
     const int ka = d0 + g * RG, kb = min(ka + RG, d1);      // dst rows owned by this group
-    const int i2lo = ka < kb ? a.bp2[ka] : 0, i2hi = ka < kb ? a.bp2[kb - 1 + S2] : 0;
-    const int nrow = i2hi - i2lo;
-    const int nrow_pad = (nrow + PF - 1) / PF * PF;         // <= R2 (host)
+    const bool active = ka < kb;
+    const int i2lo = active ? a.bp2[ka] : 0, i2hi = active ? a.bp2[kb - 1 + S2] : 0;
+    const int nrow = i2hi - i2lo;                            // <= R2 (host)
+    const int v0 = ka - (S2 - 1);                            // first dst row an accumulator slot can stand for
 
+    // ---- start streaming this thread's two src columns right away
+    const int cA = 2 * ct;
+    const int colA = r1lo + cA;
+    const bool haveA = active && cA < ncol, haveB = haveA && cA + 1 < ncol && colA + 1 < a.n1;
+    const bool vec = a.vec_ok && haveB;
+    const T *gp = src + (int64_t)i2lo * a.n1 + colA;         // next row to request
+    T *ring = sRing + 2 * tid;                               // slot d at ring + d * 2 * NT
+    int nreq = 0;                                            // rows requested so far
+    auto request = [&](T *slot) {
+        if (haveA && nreq < nrow) {
+            if (vec) {
+                cp_async<2 * sizeof(T)>(slot, gp);
+            } else {
+                cp_async<sizeof(T)>(slot, gp);
+                if (haveB) cp_async<sizeof(T)>(slot + 1, gp + 1);
+            }
+        }
+        cp_async_commit();
+        ++nreq;
+        gp += a.n1;
+    };
+#pragma unroll
+    for (int d = 0; d < D; ++d) request(ring + d * 2 * NT);
+
+    // ---- stage the small tables
+    for (int k = tid; k < NG * (RG + S2); k += NT) sNv[k] = 0;
     for (int k = tid; k < ncol; k += NT) sB1[k] = a.base1[r1lo + k];
     for (int k = tid; k < ncol * S1; k += NT) sW1[k] = a.W1[(int64_t)r1lo * S1 + k];
+    __syncthreads();
     // dim-2 rows of this group: fold the taps clamped onto dst row 0 / m2-1 into the first / last tap, so that
     // every staged window lies inside [0, m2) (needs m2 >= S2, checked by the host)
-    for (int k = ct; k < nrow_pad; k += TPG) {
-        int *bo = sB2 + g * R2 + k;
-        T *wo = sW2 + ((size_t)g * R2 + k) * S2;
-        if (k < nrow) {
-            const int b = a.base2[i2lo + k];
-            const int bc = min(max(b, 0), a.m2 - S2);
-            T w[S2];
+    for (int k = ct; k < nrow; k += TPG) {
+        const int b = a.base2[i2lo + k];
+        const int bc = min(max(b, 0), a.m2 - S2);
+        T w[S2];
 #pragma unroll
-            for (int s = 0; s < S2; ++s) w[s] = (T)0;
+        for (int s = 0; s < S2; ++s) w[s] = (T)0;
 #pragma unroll
-            for (int s = 0; s < S2; ++s) {
-                const int j = min(max(b + s, 0), a.m2 - 1) - bc;   // tap s lands in slot j of the shifted window
-                const T ws = a.alpha * a.W2[(int64_t)(i2lo + k) * S2 + s];
+        for (int s = 0; s < S2; ++s) {
+            const int jslot = min(max(b + s, 0), a.m2 - 1) - bc;   // tap s lands in slot jslot of the shifted window
+            const T ws = a.alpha * a.W2[(int64_t)(i2lo + k) * S2 + s];
 #pragma unroll
-                for (int jj = 0; jj < S2; ++jj)
-                    if (jj == j) w[jj] += ws;
-            }
-            *bo = bc;
-#pragma unroll
-            for (int s = 0; s < S2; ++s) wo[s] = w[s];
-        } else {   // padding rows: contribute nothing, do not advance the window
-            *bo = INT_MIN;
-#pragma unroll
-            for (int s = 0; s < S2; ++s) wo[s] = (T)0;
+            for (int jj = 0; jj < S2; ++jj)
+                if (jj == jslot) w[jj] += ws;
         }
+        atomicAdd(&sNv[g * (RG + S2) + max(bc, v0) - v0], 1);
+#pragma unroll
+        for (int s = 0; s < S2; ++s) sW2[((size_t)g * R2 + k) * S2 + s] = w[s];
     }
     __syncthreads();
 
-    // ---- phase 1
-    if (ka < kb) {
-        const int cA = 2 * ct;
-        const int colA = r1lo + cA;
-        const bool haveA = cA < ncol, haveB = cA + 1 < ncol && colA + 1 < a.n1;
-        const bool vec = a.vec_ok && haveB;
-        T *tp = sT + (ka - d0) * PH + ct;   // next owned row to store; plane 0 (even staged columns), plane 1 at +PLANE
-        const T *lp = src + (int64_t)i2lo * a.n1 + colA;   // next row to load
-        int left = haveA ? nrow : 0;                        // rows still to be loaded
-        auto load = [&]() {
-            Pack<T, 2> y;
-            y.v[0] = y.v[1] = (T)0;
-            if (left > 0) {
-                if (vec) {
-                    y = ld_pack<T, 2>(lp);
-                } else {
-                    y.v[0] = lp[0];
-                    if (haveB) y.v[1] = lp[1];
-                }
-            }
-            --left;
-            lp += a.n1;
-            return y;
-        };
-        Pack<T, 2> q[PF];
-#pragma unroll
-        for (int u = 0; u < PF; ++u) q[u] = load();
+    // ---- phase 1: dst rows v0, v0+1, ... of the group are finished one at a time (rows below ka are discarded)
+    if (active) {
         T A0[S2], A1[S2];
 #pragma unroll
         for (int s = 0; s < S2; ++s) A0[s] = A1[s] = (T)0;
-        int cur = ka - (S2 - 1);   // dst row of accumulator slot 0
-        // retire accumulator slot 0 (dst row `cur`), then shift
-        auto retire = [&]() {
-            if (cur >= ka) {
-                tp[0] = A0[0];
-                tp[PLANE] = A1[0];
-                tp += PH;
-            }
+        const int *pn = sNv + g * (RG + S2);
+        const T *pw = sW2 + (size_t)g * R2 * S2;
+        T *tp = sT + (ka - d0) * PH + ct;   // plane 0 (even staged columns); plane 1 at +PLANE
+        int rd = 0;                         // ring slot of the next row to consume
+        T *prev = nullptr;                  // slot consumed one row ago: refilled now (its load has long completed)
+        for (int v = v0; v < kb; v += S2) {
 #pragma unroll
-            for (int s = 0; s + 1 < S2; ++s) {
-                A0[s] = A0[s + 1];
-                A1[s] = A1[s + 1];
-            }
-            A0[S2 - 1] = A1[S2 - 1] = (T)0;
-            ++cur;
-        };
-        const int *bq = sB2 + g * R2;
-        const T *wq = sW2 + (size_t)g * R2 * S2;
-        for (int k = 0; k < nrow_pad; k += PF) {
+            for (int u = 0; u < S2; ++u) {
+                const int vv = v + u;
+                if (vv < kb) {
+                    // add every src row whose window starts at dst row vv: tap s goes to slot (u + s) % S2
+                    for (int n = *pn++; n > 0; --n) {
+                        cp_async_wait<D - 2>();
+                        T *slot = ring + rd * 2 * NT;
+                        const Pack<T, 2> y = ld_pack<T, 2>(slot);
+                        if (prev) request(prev);
+                        prev = slot;
+                        if (++rd == D) rd = 0;
+                        T w[S2];
+                        ld_weights<T, S2>(pw, w);
+                        pw += S2;
 #pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const Pack<T, 2> y = q[u];
-                q[u] = load();
-                const int b = bq[k + u];
-                while (cur < b) retire();
-                T w[S2];
-                ld_weights<T, S2>(wq + (k + u) * S2, w);
-#pragma unroll
-                for (int s = 0; s < S2; ++s) {
-                    A0[s] = fmaT(w[s], y.v[0], A0[s]);
-                    A1[s] = fmaT(w[s], y.v[1], A1[s]);
+                        for (int s = 0; s < S2; ++s) {
+                            A0[(u + s) % S2] = fmaT(w[s], y.v[0], A0[(u + s) % S2]);
+                            A1[(u + s) % S2] = fmaT(w[s], y.v[1], A1[(u + s) % S2]);
+                        }
+                    }
+                    if (vv >= ka) {   // dst row vv is complete
+                        tp[0] = A0[u];
+                        tp[PLANE] = A1[u];
+                        tp += PH;
+                    }
+                    A0[u] = A1[u] = (T)0;
                 }
             }
         }
-        while (cur < kb) retire();
     }
+    cp_async_wait<0>();
     __syncthreads();
 
     // ---- phase 2: gather along dim 1; NT threads = NSL row slices x CT dst columns
@@ -496,28 +508,31 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1)
         constexpr int CT = 128, NSL = NT / CT, RS = TD2 / NSL;   // RS rows per slice
         const int kc = tid % CT, sl = tid / CT;
         const int nr = min(RS, d1 - d0 - sl * RS);               // valid rows of this slice
-        for (int kk = kc; kk < c1 - c0 && nr > 0; kk += CT) {
-            const int k1 = c0 + kk;
+        for (int kk0 = kc; kk0 < c1 - c0 && nr > 0; kk0 += CT) {
+            const int k1 = c0 + kk0;
             const int e0 = a.bp1[k1] - r1lo, e1 = a.bp1[k1 + S1] - r1lo;   // contributing staged src columns
             const T *rowbase = sT + sl * RS * PH;
-            T *d = dst + (int64_t)(d0 + sl * RS) * a.m1 + k1;
             T acc[RS];
 #pragma unroll
             for (int r = 0; r < RS; ++r) acc[r] = (T)0;
-            // interior columns: one tap per src column (static register indexing); edge columns carry the
-            // clamped taps of every out-of-range src column and take the generic loop, as do very long lists
+            // interior columns: one tap per src column; tap k reads staged column c = e0 + k, stored in plane
+            // (c & 1) at index (c >> 1): with q = e0 & 1 the even taps live at pE[k/2], the odd ones at pO[(k-1)/2]
             const bool interior = k1 > 0 && k1 < a.m1 - 1;
             const int cnt = interior ? min(e1 - e0, ADJ_MAXE) : 0;
+            const int q0 = e0 & 1;
+            const T *pE = rowbase + q0 * PLANE + (e0 >> 1);
+            const T *pO = rowbase + (1 - q0) * PLANE + (e0 >> 1) + q0;
 #pragma unroll
             for (int k = 0; k < ADJ_MAXE; ++k) {
                 if (k < cnt) {
-                    const int c = e0 + k;
-                    const T wk = sW1[c * S1 + (k1 - sB1[c])];
-                    const T *p = rowbase + (c & 1) * PLANE + (c >> 1);
+                    const T wk = sW1[(e0 + k) * S1 + (k1 - sB1[e0 + k])];
+                    const T *p = (k & 1) ? pO + (k - 1) / 2 : pE + k / 2;
 #pragma unroll
                     for (int r = 0; r < RS; ++r) acc[r] = fmaT(wk, p[r * PH], acc[r]);
                 }
             }
+            // edge columns carry the clamped taps of every out-of-range src column; they and very long tap
+            // lists take this generic loop
             for (int e = e0 + cnt; e < e1; ++e) {
                 const int b = sB1[e];
                 int slo = k1 - b, shi = k1 - b;   // taps s with clamp(b + s) == k1
@@ -532,6 +547,7 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1)
                     for (int r = 0; r < RS; ++r) acc[r] = fmaT(ws, p[r * PH], acc[r]);
                 }
             }
+            T *d = dst + (int64_t)(d0 + sl * RS) * a.m1 + k1;
 #pragma unroll
             for (int r = 0; r < RS; ++r) {
                 if (r < nr) {
@@ -613,7 +629,7 @@ template <typename T, int S1, int S2>
 static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64_t nbatch, cudaStream_t st,
                       bool *done)
 {
-    constexpr int NG = 2, PT = 2 * (ADJ_NT / NG), RG = ADJ_TD2 / NG;
+    constexpr int NG = ADJ_NG, PT = 2 * (ADJ_NT / NG), RG = ADJ_TD2 / NG;
     if (a.m2 < S2 || a.m1 < 2) return LI_OK;   // decline: the edge folding needs a full window inside the array
     int rc = table_ensure_rowstart(t1, st);
     if (rc == LI_OK) rc = table_ensure_rowstart(t2, st);
@@ -635,24 +651,26 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     int r2 = 0;
     rc = table_adj_rows(t2, RG, st, &r2);
     if (rc != LI_OK) return rc;
-    a.F2MAX = (r2 + ADJ_PF - 1) / ADJ_PF * ADJ_PF;
+    if (r2 > 2048) return LI_OK;   // decline (heavy down-sampling along dim 2)
+    const int R2 = std::max(r2, 1);
     a.tiles1 = (a.m1 + TD1 - 1) / TD1, a.tiles2 = (a.m2 + ADJ_TD2 - 1) / ADJ_TD2;
     a.vec_ok = (a.n1 % 2 == 0) && (((uintptr_t)a.src) % (2 * sizeof(T)) == 0);
-    const size_t smem = (2 * ((size_t)ADJ_TD2 * (PT / 2) + 16) + (size_t)PT * S1 + (size_t)NG * a.F2MAX * S2) * sizeof(T) +
-                        ((size_t)PT + (size_t)NG * a.F2MAX) * sizeof(int);
+    const size_t smem = (2 * ((size_t)ADJ_TD2 * (PT / 2) + 16) + (size_t)ADJ_D * ADJ_NT * 2 + (size_t)PT * S1 +
+                         (size_t)NG * R2 * S2) * sizeof(T) +
+                        ((size_t)PT + (size_t)NG * (RG + S2)) * sizeof(int);
     if (smem > (size_t)kSmemLimit) return LI_OK;
     const int64_t blocks = (int64_t)a.tiles1 * a.tiles2 * nbatch;
     LI_REQUIRE(blocks <= 0x7fffffffLL, LI_ERR_UNSUPPORTED, "too many tiles");
     if (a.beta != (T)0) {
-        auto kern = sep2d_adj_kernel<T, S1, S2, NG, true>;
+        auto kern = sep2d_adj_kernel<T, S1, S2, true>;
         rc = set_smem(kern, smem);
         if (rc != LI_OK) return rc;
-        kern<<<(unsigned)blocks, ADJ_NT, smem, st>>>(a, TD1);
+        kern<<<(unsigned)blocks, ADJ_NT, smem, st>>>(a, TD1, R2);
     } else {
-        auto kern = sep2d_adj_kernel<T, S1, S2, NG, false>;
+        auto kern = sep2d_adj_kernel<T, S1, S2, false>;
         rc = set_smem(kern, smem);
         if (rc != LI_OK) return rc;
-        kern<<<(unsigned)blocks, ADJ_NT, smem, st>>>(a, TD1);
+        kern<<<(unsigned)blocks, ADJ_NT, smem, st>>>(a, TD1, R2);
     }
     LI_CHECK_LAUNCH();
     *done = true;
