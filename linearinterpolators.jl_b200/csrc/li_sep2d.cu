@@ -407,29 +407,40 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1, const int R2 /* staged dim-2
     const int nrow = i2hi - i2lo;                            // <= R2 (host)
     const int v0 = ka - (S2 - 1);                            // first dst row an accumulator slot can stand for
 
-    // ---- start streaming this thread's two src columns right away
+    // ---- start streaming this thread's two src columns right away.  Ring slot of row k: byte offset
+    // (k * SLOT) & (D * SLOT - 1) from ring_u32 (D is a power of two): no wrap branch, no pointer table.
+    static_assert((D & (D - 1)) == 0, "ring depth must be a power of two");
+    constexpr uint32_t SLOT = 2u * NT * (uint32_t)sizeof(T);   // bytes between consecutive ring slots
+    constexpr uint32_t RMASK = D * SLOT - 1u;
     const int cA = 2 * ct;
     const int colA = r1lo + cA;
     const bool haveA = active && cA < ncol, haveB = haveA && cA + 1 < ncol && colA + 1 < a.n1;
     const bool vec = a.vec_ok && haveB;
     const T *gp = src + (int64_t)i2lo * a.n1 + colA;         // next row to request
-    T *ring = sRing + 2 * tid;                               // slot d at ring + d * 2 * NT
-    int nreq = 0;                                            // rows requested so far
-    auto request = [&](T *slot) {
-        if (haveA && nreq < nrow) {
-            if (vec) {
-                cp_async<2 * sizeof(T)>(slot, gp);
-            } else {
-                cp_async<sizeof(T)>(slot, gp);
-                if (haveB) cp_async<sizeof(T)>(slot + 1, gp + 1);
+    const uint32_t ring_u32 = smem_u32(sRing + 2 * tid);
+    const int64_t gstep = (int64_t)a.n1 * (int64_t)sizeof(T);
+    int togo = haveA ? nrow : 0;                             // rows still to be requested
+    // request the next row into the slot at byte offset `off` (predicated, branch-free in the vector case)
+    auto request = [&](uint32_t off) {
+        if (vec) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %2, 0;\n\t"
+                "@p cp.async.ca.shared.global [%0], [%1], %3;\n\t"
+                "cp.async.commit_group;\n\t}" ::"r"(ring_u32 + off),
+                "l"(gp), "r"(togo), "n"(2 * sizeof(T))
+                : "memory");
+        } else {
+            if (togo > 0) {
+                cp_async<sizeof(T)>(sRing + 2 * tid + off / sizeof(T), gp);
+                if (haveB) cp_async<sizeof(T)>(sRing + 2 * tid + off / sizeof(T) + 1, gp + 1);
             }
+            cp_async_commit();
         }
-        cp_async_commit();
-        ++nreq;
-        gp += a.n1;
+        --togo;
+        gp = reinterpret_cast<const T *>(reinterpret_cast<const char *>(gp) + gstep);
     };
 #pragma unroll
-    for (int d = 0; d < D; ++d) request(ring + d * 2 * NT);
+    for (int d = 0; d < D; ++d) request((uint32_t)d * SLOT);
 
     // ---- stage the small tables
     for (int k = tid; k < NG * (RG + S2); k += NT) sNv[k] = 0;
@@ -466,8 +477,9 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1, const int R2 /* staged dim-2
         const int *pn = sNv + g * (RG + S2);
         const T *pw = sW2 + (size_t)g * R2 * S2;
         T *tp = sT + (ka - d0) * PH + ct;   // plane 0 (even staged columns); plane 1 at +PLANE
-        int rd = 0;                         // ring slot of the next row to consume
-        T *prev = nullptr;                  // slot consumed one row ago: refilled now (its load has long completed)
+        uint32_t roff = 0;                  // ring byte offset of the next row to consume
+        uint32_t woff = 0;                  // byte offset of the next row's weights
+        bool first = true;
         for (int v = v0; v < kb; v += S2) {
 #pragma unroll
             for (int u = 0; u < S2; ++u) {
@@ -476,14 +488,18 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1, const int R2 /* staged dim-2
                     // add every src row whose window starts at dst row vv: tap s goes to slot (u + s) % S2
                     for (int n = *pn++; n > 0; --n) {
                         cp_async_wait<D - 2>();
-                        T *slot = ring + rd * 2 * NT;
-                        const Pack<T, 2> y = ld_pack<T, 2>(slot);
-                        if (prev) request(prev);
-                        prev = slot;
-                        if (++rd == D) rd = 0;
+                        Pack<T, 2> y;
+                        if constexpr (sizeof(T) == 4)
+                            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(y.v[0]), "=f"(y.v[1]) : "r"(ring_u32 + roff));
+                        else
+                            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(y.v[0]), "=d"(y.v[1]) : "r"(ring_u32 + roff));
+                        // refill the slot consumed one row ago (its load has long completed)
+                        if (!first) request((roff - SLOT) & RMASK);
+                        first = false;
+                        roff = (roff + SLOT) & RMASK;
                         T w[S2];
-                        ld_weights<T, S2>(pw, w);
-                        pw += S2;
+                        ld_weights<T, S2>(reinterpret_cast<const T *>(reinterpret_cast<const char *>(pw) + woff), w);
+                        woff += S2 * sizeof(T);
 #pragma unroll
                         for (int s = 0; s < S2; ++s) {
                             A0[(u + s) % S2] = fmaT(w[s], y.v[0], A0[(u + s) % S2]);

@@ -2,7 +2,7 @@ import csv, sys
 from collections import Counter
 rows=list(csv.reader(open(sys.argv[1])))
 hdr=rows[1]; data=[r for r in rows[2:] if len(r)>=len(hdr)-2 and r[0].startswith('0x')]
-n=len(data)//2; data=data[:n]
+n=len(data) if len(sys.argv)>4 else len(data)//2; data=data[:n]
 iS=hdr.index("Source"); iE=hdr.index("Instructions Executed"); iSt=hdr.index("# Samples")
 tot=sum(int(r[iE]) for r in data); ts=sum(int(r[iSt]) for r in data)
 ncta=int(sys.argv[2]); print("warp-instr per CTA", tot/ncta, "n sass", n)
