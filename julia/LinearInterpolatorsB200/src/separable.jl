@@ -1,0 +1,54 @@
+# separable.jl -- 2-D separable apply! with on-the-fly coefficients (reference: src/separable.jl) and the fused
+# product of per-dimension table operators.
+
+function apply!(α::Real, ::Type{P}, ker1::Kernel{T,S1}, x1::AbstractVector{T}, ker2::Kernel{T,S2},
+                x2::AbstractVector{T}, src::AbstractArray{T,2}, β::Real,
+                dst::AbstractArray{T,2}) where {P<:Union{Direct,Adjoint},T<:Floats,S1,S2}
+    n1, n2 = length(x1), length(x2)
+    if P === Direct
+        @assert size(dst) == (n1, n2)
+        m1, m2 = size(src)
+    else
+        @assert size(src) == (n1, n2)
+        m1, m2 = size(dst)
+    end
+    d1, d2 = DeviceArray(collect(x1)), DeviceArray(collect(x2))
+    dsrc, ddst = DeviceArray(convert(Array{T}, src)), DeviceArray(convert(Array{T}, dst))
+    k1, k2 = Ref(kernel_desc(ker1)), Ref(kernel_desc(ker2))
+    check(ccall((:li_sep2d_otf_apply, LIB), Cint,
+                (Cint, Ptr{KernelDesc}, Ptr{Cvoid}, Int64, Ptr{KernelDesc}, Ptr{Cvoid}, Int64, Int64, Int64, Int64,
+                 Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid}),
+                P === Adjoint, k1, d1, n1, k2, d2, n2, m1, m2, 1, α, dsrc, β, ddst, C_NULL))
+    copyto!(dst, Array(ddst))
+    return dst
+end
+
+"""
+    sep_apply!(α, P, (A1, A2[, A3]), x, β, y)
+
+applies `A1*A2[*A3]` (or its adjoint), `Ak` interpolating dimension `k`, in one call of `li_sep_apply[_host]`
+(a single fused pass over HBM for two dimensions).
+"""
+function sep_apply!(α::Real, ::Type{P}, As::Tuple{Vararg{PerDim}}, x::HostOrDevice{T,N}, β::Real,
+                    y::HostOrDevice{T,N}) where {P<:Union{Direct,Adjoint},T,N}
+    length(As) == N || throw(DimensionMismatch("one operator per dimension is required"))
+    all(k -> interp_dim(As[k]) == k, 1:N) || error("operator k must interpolate dimension k")
+    handles = Ptr{Cvoid}[A.table.handle for A in As]
+    dims = Int64[size(x)...]
+    if x isa DeviceArray
+        need = Ref{Csize_t}(0)
+        check(ccall((:li_sep_workspace_bytes, LIB), Cint, (Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Int64, Ptr{Csize_t}),
+                    P === Adjoint, N, handles, dims, 1, need))
+        ws = DeviceArray{UInt8,1}(undef, (Int(need[]) + 1,))
+        check(ccall((:li_sep_apply, LIB), Cint,
+                    (Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Int64, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid},
+                     Csize_t, Cint, Ptr{Cvoid}),
+                    P === Adjoint, N, handles, dims, 1, α, x, β, y, ws, need[], 0, C_NULL))
+        check(ccall((:li_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+    else
+        check(ccall((:li_sep_apply_host, LIB), Cint,
+                    (Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Int64, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                    P === Adjoint, N, handles, dims, 1, α, x, β, y, 0, C_NULL))
+    end
+    return y
+end

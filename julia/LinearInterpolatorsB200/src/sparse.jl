@@ -1,0 +1,92 @@
+# sparse.jl -- SparseInterpolator / SparseUnidimensionalInterpolator over the same device tables
+# (reference: src/sparse.jl).  AtA / fit / regularize are out of scope (dense normal equations, not interpolation).
+
+abstract type AbstractSparseInterpolator{T<:AbstractFloat} <: LinearMapping end
+Base.eltype(::AbstractSparseInterpolator{T}) where {T} = T
+
+# positions -> fractional indices, evaluated in T on the host exactly like the reference's closure
+function fractional_index(::Type{T}, pos::AbstractArray{<:Real}, grd::AbstractRange) where {T<:AbstractFloat}
+    c = (convert(T, first(grd)) + convert(T, last(grd))) / 2
+    q = 1 / convert(T, step(grd))
+    r = convert(T, 1 + length(grd)) / 2
+    return T[q * (convert(T, p) - c) + r for p in vec(pos)]
+end
+fractional_index(::Type{T}, pos::AbstractArray{<:Real}) where {T<:AbstractFloat} = T[T(p) for p in vec(pos)]
+
+struct SparseInterpolator{T<:AbstractFloat,S,N} <: AbstractSparseInterpolator{T}
+    table::Table{T}
+    nrows::Int
+    ncols::Int
+    dims::Dims{N}
+end
+(A::SparseInterpolator)(x::AbstractVector) = apply(A, x)
+output_size(A::SparseInterpolator) = A.dims
+input_size(A::SparseInterpolator) = (A.ncols,)
+coefficients(A::AbstractSparseInterpolator) = vec(export!(A.table).W)
+columns(A::AbstractSparseInterpolator) = vec(export!(A.table).J)
+
+SparseInterpolator(ker::Kernel{T}, args...) where {T<:AbstractFloat} = SparseInterpolator{T}(ker, args...)
+SparseInterpolator{T}(ker::Kernel, args...) where {T<:AbstractFloat} = SparseInterpolator{T}(T(ker), args...)
+SparseInterpolator{T}(ker::Kernel{T,S}, pos::AbstractArray{<:Real,N}, grd::AbstractRange) where {T<:Floats,S,N} =
+    SparseInterpolator{T,S,N}(Table(ker, fractional_index(T, pos, grd), length(grd)), length(pos), length(grd), size(pos))
+SparseInterpolator{T}(ker::Kernel{T,S}, pos::AbstractArray{<:Real,N}, len::Integer) where {T<:Floats,S,N} =
+    SparseInterpolator{T,S,N}(Table(ker, fractional_index(T, pos), len), length(pos), Int(len), size(pos))
+
+vcreate(::Type{Direct}, A::SparseInterpolator{T}, x::HostOrDevice{T,1}, scratch::Bool=false) where {T} =
+    similar_array(x, T, A.dims)
+vcreate(::Type{Adjoint}, A::SparseInterpolator{T,S,N}, x::HostOrDevice{T,N}, scratch::Bool=false) where {T,S,N} =
+    similar_array(x, T, (A.ncols,))
+
+function apply!(α::Real, ::Type{P}, A::SparseInterpolator{T,S,N}, x::HostOrDevice{T}, scratch::Bool, β::Real,
+                y::HostOrDevice{T}) where {P<:Union{Direct,Adjoint},T,S,N}
+    inp, out = P === Direct ? (x, y) : (y, x)
+    length(inp) == A.ncols || error("bad vector length (expecting $(A.ncols), got $(length(inp)))")
+    size(out) == A.dims || error("bad output array size (expecting $(A.dims), got $(size(out)))")
+    tab_apply!(P === Adjoint, A.table, 1, 1, α, x, β, y)
+    return y
+end
+
+struct SparseUnidimensionalInterpolator{T<:AbstractFloat,S,D} <: AbstractSparseInterpolator{T}
+    nrows::Int
+    ncols::Int
+    table::Table{T}
+end
+(A::SparseUnidimensionalInterpolator)(x) = apply(A, x)
+Base.size(A::SparseUnidimensionalInterpolator) = (A.nrows, A.ncols)
+
+SparseUnidimensionalInterpolator(ker::Kernel{T}, args...) where {T<:AbstractFloat} =
+    SparseUnidimensionalInterpolator{T}(ker, args...)
+SparseUnidimensionalInterpolator{T}(ker::Kernel, args...) where {T<:AbstractFloat} =
+    SparseUnidimensionalInterpolator{T}(T(ker), args...)
+function SparseUnidimensionalInterpolator{T}(ker::Kernel{T}, d::Integer, pos::AbstractVector{<:Real},
+                                             len::Integer) where {T<:Floats}
+    len ≥ 1 || throw(ArgumentError("invalid dimension length"))
+    return SparseUnidimensionalInterpolator{T}(ker, d, pos, 1:Int(len))
+end
+function SparseUnidimensionalInterpolator{T}(ker::Kernel{T,S}, d::Integer, pos::AbstractVector{<:Real},
+                                             grd::AbstractRange) where {T<:Floats,S}
+    d ≥ 1 || throw(ArgumentError("invalid dimension of interpolation"))
+    tbl = Table(ker, fractional_index(T, pos, grd), length(grd))
+    return SparseUnidimensionalInterpolator{T,S,Int(d)}(length(pos), length(grd), tbl)
+end
+
+function _shape(A::SparseUnidimensionalInterpolator{T,S,D}, P, x::AbstractArray{<:Any,N}) where {T,S,D,N}
+    1 ≤ D ≤ N || throw(DimensionMismatch("out of range dimension of interpolation"))
+    nx, ny = P === Direct ? (A.ncols, A.nrows) : (A.nrows, A.ncols)
+    size(x, D) == nx || throw(DimensionMismatch("dimension $D of `x` must be $nx"))
+    return ntuple(i -> (i == D ? ny : size(x, i)), Val(N))
+end
+vcreate(::Type{P}, A::SparseUnidimensionalInterpolator{T}, x::HostOrDevice{T}, scratch::Bool=false) where {P<:Union{Direct,Adjoint},T} =
+    similar_array(x, T, _shape(A, P, x))
+function apply!(α::Real, ::Type{P}, A::SparseUnidimensionalInterpolator{T,S,D}, x::HostOrDevice{T,N}, scratch::Bool,
+                β::Real, y::HostOrDevice{T,N}) where {P<:Union{Direct,Adjoint},T,S,D,N}
+    size(y) == _shape(A, P, x) || throw(DimensionMismatch("`x` and `y` have incompatible dimensions"))
+    tab_apply!(P === Adjoint, A.table, prod(size(x)[1:D-1]), prod(size(x)[D+1:N]), α, x, β, y)
+    return y
+end
+
+# H = A1*A2 of per-dimension operators: one fused pass through li_sep_apply instead of LazyAlgebra's generic
+# composition (which would allocate an intermediate and make two passes).
+const PerDim = Union{TabulatedInterpolator,SparseUnidimensionalInterpolator}
+interp_dim(A::TabulatedInterpolator) = A.d
+interp_dim(::SparseUnidimensionalInterpolator{T,S,D}) where {T,S,D} = D
