@@ -20,6 +20,7 @@ from .separable import sep2d_otf_apply, sep_apply_tables
 from .sparse import Range, SparseInterpolator, SparseUnidimensionalInterpolator, fractional_index
 from .tabulated import TabulatedInterpolator, coefficients, columns, ncols, nrows, width
 from .unidimensional import otf1d_apply
+from .distributed import accumulate_adjoint, shard_range, world_info
 
 
 def getcoefs(ker, length, x):
