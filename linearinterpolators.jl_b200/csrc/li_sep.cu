@@ -95,6 +95,31 @@ static int sep_apply_impl(int adjoint, int ndim, const li_table *const *tabs, co
     sep_workspace(plan, dtype, &need, &half);
     LI_REQUIRE(workspace_bytes >= need && (need == 0 || workspace), LI_ERR_ARG,
                "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+
+    // three dimensions: the pass along dim 3 on its own, dims 1 and 2 fused with dim 3 as the batch (2 passes over
+    // HBM instead of 3)
+    if (ndim == 3 && tabs[0] && tabs[1] && tabs[2] && variant != LI_VARIANT_ATOMIC &&
+        sep2d_fused_supported(tabs[0], tabs[1])) {
+        const li_table *t1 = tabs[0], *t2 = tabs[1], *t3 = tabs[2];
+        bool done = false;
+        if (!adjoint) {
+            // A3 first: [m1, m2, m3] -> ws [m1, m2, n3]; then A1*A2 on every slice
+            rc = tab_apply_impl(0, t3, t1->ncols * t2->ncols, nbatch, 1.0, src, 0.0, workspace, variant, st);
+            if (rc != LI_OK) return rc;
+            rc = sep2d_fused_apply(0, t1, t2, t3->nrows * nbatch, alpha, workspace, beta, dst, st, &done);
+            if (rc != LI_OK || done) return rc;
+            // declined: finish with the remaining per-dimension passes
+            void *ws2 = (char *)workspace + half;
+            rc = tab_apply_impl(0, t2, t1->ncols, t3->nrows * nbatch, 1.0, workspace, 0.0, ws2, variant, st);
+            if (rc != LI_OK) return rc;
+            return tab_apply_impl(0, t1, 1, t2->nrows * t3->nrows * nbatch, alpha, ws2, beta, dst, variant, st);
+        } else {
+            // (A1*A2)' on every slice: [n1, n2, n3] -> ws [m1, m2, n3]; then A3'
+            rc = sep2d_fused_apply(1, t1, t2, t3->nrows * nbatch, 1.0, src, 0.0, workspace, st, &done);
+            if (rc != LI_OK) return rc;
+            if (done) return tab_apply_impl(1, t3, t1->ncols * t2->ncols, nbatch, alpha, workspace, beta, dst, variant, st);
+        }
+    }
     const void *in = src;
     for (int p = 0; p < plan.npass; ++p) {
         const bool last = p == plan.npass - 1;
