@@ -31,6 +31,16 @@ def world_info():
     return 0, 1
 
 
+def _dense(t):
+    """A contiguous view of the same memory (collectives need one): column-major arrays are permuted views."""
+    if t.is_contiguous():
+        return t
+    tt = t.permute(*reversed(range(t.ndim)))
+    if not tt.is_contiguous():
+        raise ValueError("accumulator must be a dense row- or column-major tensor")
+    return tt
+
+
 def accumulate_adjoint(nframes: int, adjoint_into: Callable[[int, object], None], acc, *, groups: int = 1,
                        group=None, comm_stream=None):
     """``acc <- sum over ALL ranks and frames k of A_k' y_k``.
@@ -52,7 +62,7 @@ def accumulate_adjoint(nframes: int, adjoint_into: Callable[[int, object], None]
         for k in range(lo, hi):
             adjoint_into(k, acc)
         if world > 1:
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(_dense(acc), op=dist.ReduceOp.SUM, group=group)
         return acc
     # overlapped variant
     n_local = hi - lo
@@ -70,9 +80,9 @@ def accumulate_adjoint(nframes: int, adjoint_into: Callable[[int, object], None]
             ev.record(cur)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev)
-                works.append(dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group, async_op=True))
+                works.append(dist.all_reduce(_dense(part), op=dist.ReduceOp.SUM, group=group, async_op=True))
         else:
-            works.append(dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group, async_op=True))
+            works.append(dist.all_reduce(_dense(part), op=dist.ReduceOp.SUM, group=group, async_op=True))
         parts.append(part)
     for w in works:
         w.wait()
