@@ -68,6 +68,11 @@ struct li_table {
     mutable int32_t *tent = nullptr;    // [nrows*S] entry id e = row*S + tap
     // monotone windowed tables: bptr[j] = first row with base >= j-(S-1), j in [0, ncols+S-1] (see li_table.cu)
     mutable int32_t *rowstart = nullptr;
+    // adjoint of the fused kernels: windows folded into [0, ncols) (clamped taps merged into the first/last tap)
+    mutable void *Wfold = nullptr;      // [nrows*S] folded weights
+    mutable int32_t *bfold = nullptr;   // [nrows] folded window bases, in [0, ncols - S]
+    mutable int32_t *bpf = nullptr;     // bptr table over bfold, [ncols + S]
+    mutable std::map<int, int> adjf_rows;
     // cached footprint bounds: key = tile rows G -> max over aligned tiles of (max base - min base)
     mutable std::map<int, int> fwd_span;
     // cached: key = tile cols G -> max over aligned column tiles of number of contributing rows
@@ -79,6 +84,8 @@ int table_ensure_csc(const li_table *t, cudaStream_t st);
 int table_ensure_rowstart(const li_table *t, cudaStream_t st);
 int table_fwd_span(const li_table *t, int G, cudaStream_t st, int *span);
 int table_adj_rows(const li_table *t, int G, cudaStream_t st, int *rows);
+int table_ensure_fold(const li_table *t, cudaStream_t st);            // needs ncols >= S
+int table_adjf_rows(const li_table *t, int G, cudaStream_t st, int *rows);  // like table_adj_rows, folded bases
 // builds a table from device positions into preallocated device arrays (used by the OTF operators)
 int table_create_impl(const li_kernel_desc *ker, const void *pos_dev, int64_t nrows, int64_t ncols,
                       cudaStream_t st, li_table **out);

@@ -75,7 +75,8 @@ template <typename T>
 struct SepArgs {
     const int32_t *base1, *base2;  // window bases (canonical, 0-based)
     const T *W1, *W2;              // [n*S]
-    const int32_t *bp1, *bp2;      // adjoint only: bptr tables (see li_table.cu), [m+S]
+    const int32_t *bp1, *bp2;      // adjoint only: bptr tables (see li_table.cu), [m+S]; bp2 is over FOLDED bases
+    const T *W2f;                  // adjoint only: folded dim-2 weights (li_table.cu: fold_kernel)
     int n1, n2;                    // "rows" side (fine grid for an upsampling operator)
     int m1, m2;                    // "columns" side
     int tiles1, tiles2;
@@ -442,30 +443,14 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1, const int R2 /* staged dim-2
 #pragma unroll
     for (int d = 0; d < D; ++d) request((uint32_t)d * SLOT);
 
-    // ---- stage the small tables
-    for (int k = tid; k < NG * (RG + S2); k += NT) sNv[k] = 0;
+    // ---- stage the small tables (plain copies: the folding of the clamped dim-2 taps is precomputed per table)
     for (int k = tid; k < ncol; k += NT) sB1[k] = a.base1[r1lo + k];
     for (int k = tid; k < ncol * S1; k += NT) sW1[k] = a.W1[(int64_t)r1lo * S1 + k];
-    __syncthreads();
-    // dim-2 rows of this group: fold the taps clamped onto dst row 0 / m2-1 into the first / last tap, so that
-    // every staged window lies inside [0, m2) (needs m2 >= S2, checked by the host)
-    for (int k = ct; k < nrow; k += TPG) {
-        const int b = a.base2[i2lo + k];
-        const int bc = min(max(b, 0), a.m2 - S2);
-        T w[S2];
-#pragma unroll
-        for (int s = 0; s < S2; ++s) w[s] = (T)0;
-#pragma unroll
-        for (int s = 0; s < S2; ++s) {
-            const int jslot = min(max(b + s, 0), a.m2 - 1) - bc;   // tap s lands in slot jslot of the shifted window
-            const T ws = a.alpha * a.W2[(int64_t)(i2lo + k) * S2 + s];
-#pragma unroll
-            for (int jj = 0; jj < S2; ++jj)
-                if (jj == jslot) w[jj] += ws;
-        }
-        atomicAdd(&sNv[g * (RG + S2) + max(bc, v0) - v0], 1);
-#pragma unroll
-        for (int s = 0; s < S2; ++s) sW2[((size_t)g * R2 + k) * S2 + s] = w[s];
+    for (int k = ct; k < nrow * S2; k += TPG) sW2[(size_t)g * R2 * S2 + k] = a.W2f[(int64_t)i2lo * S2 + k];
+    // src rows whose (folded) window starts at dst row v0 + k; rows above the last full window have none
+    for (int k = ct; k < RG + S2; k += TPG) {
+        const int v = v0 + k;
+        sNv[g * (RG + S2) + k] = (active && v >= 0 && v < kb) ? a.bp2[v + S2] - a.bp2[v + S2 - 1] : 0;
     }
     __syncthreads();
 
@@ -569,9 +554,9 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1, const int R2 /* staged dim-2
                 if (r < nr) {
                     T *dr = d + (int64_t)r * a.m1;
                     if constexpr (BETA)
-                        *dr = fmaT(a.beta, *dr, acc[r]);
+                        *dr = fmaT(a.beta, *dr, a.alpha * acc[r]);
                     else
-                        *dr = acc[r];
+                        *dr = a.alpha * acc[r];
                 }
             }
         }
@@ -648,9 +633,10 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     constexpr int NG = ADJ_NG, PT = 2 * (ADJ_NT / NG), RG = ADJ_TD2 / NG;
     if (a.m2 < S2 || a.m1 < 2) return LI_OK;   // decline: the edge folding needs a full window inside the array
     int rc = table_ensure_rowstart(t1, st);
-    if (rc == LI_OK) rc = table_ensure_rowstart(t2, st);
+    if (rc == LI_OK) rc = table_ensure_fold(t2, st);
     if (rc != LI_OK) return rc;
-    a.bp1 = t1->rowstart, a.bp2 = t2->rowstart;
+    a.bp1 = t1->rowstart, a.bp2 = t2->bpf;
+    a.W2f = (const T *)t2->Wfold;
     // widest dst tile whose contributing src columns fit the staged width
     int TD1 = 0;
     const int cands[] = {128, 120, 112, 96, 80, 64, 56, 48, 32, 24, 16, 8};
@@ -665,7 +651,7 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     }
     if (TD1 == 0) return LI_OK;   // decline
     int r2 = 0;
-    rc = table_adj_rows(t2, RG, st, &r2);
+    rc = table_adjf_rows(t2, RG, st, &r2);
     if (rc != LI_OK) return rc;
     if (r2 > 2048) return LI_OK;   // decline (heavy down-sampling along dim 2)
     const int R2 = std::max(r2, 1);

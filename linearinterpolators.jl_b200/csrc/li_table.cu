@@ -194,6 +194,23 @@ __global__ void adj_rows_kernel(const int32_t *__restrict__ bptr, int S, int nco
     atomicMax(out, (int)(bptr[k1 - 1 + S] - bptr[k0]));
 }
 
+// Fold the clamped taps of a window into the window shifted inside [0, ncols): bc = clamp(base, 0, ncols - S),
+// tap s lands in slot clamp(base + s, 0, ncols-1) - bc.  (Sums of weights that hit the same column.)
+template <typename T>
+__global__ void fold_kernel(const int32_t *__restrict__ base, const T *__restrict__ W, int64_t nrows, int S, int ncols,
+                            int32_t *__restrict__ bfold, T *__restrict__ Wfold)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int b = base[i];
+    const int bc = min(max(b, 0), ncols - S);
+    T w[LI_MAX_S];
+    for (int s = 0; s < S; ++s) w[s] = (T)0;
+    for (int s = 0; s < S; ++s) w[min(max(b + s, 0), ncols - 1) - bc] += W[i * S + s];
+    bfold[i] = bc;
+    for (int s = 0; s < S; ++s) Wfold[i * S + s] = w[s];
+}
+
 __global__ void iota_keys_kernel(const int32_t *__restrict__ J, int64_t n, int32_t *__restrict__ keys,
                                  int32_t *__restrict__ vals)
 {
@@ -364,6 +381,40 @@ int table_ensure_rowstart(const li_table *t, cudaStream_t st)
     return LI_OK;
 }
 
+int table_ensure_fold(const li_table *t, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lock(t->mu);
+    if (t->bpf) return LI_OK;
+    LI_REQUIRE(t->windowed && t->monotone && t->ncols >= t->S, LI_ERR_ARG, "folding needs a monotone windowed table with ncols >= S");
+    void *wf = nullptr;
+    int32_t *bf = nullptr, *bp = nullptr;
+    cudaError_t e = cudaMalloc(&wf, (size_t)t->nrows * t->S * dtype_size(t->dtype));
+    if (e == cudaSuccess) e = cudaMalloc(&bf, (size_t)t->nrows * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&bp, (size_t)(t->ncols + t->S) * sizeof(int32_t));
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((t->nrows + 127) / 128);
+        if (t->dtype == LI_F32)
+            fold_kernel<float><<<blocks, 128, 0, st>>>(t->base, (const float *)t->W, t->nrows, t->S, (int)t->ncols, bf, (float *)wf);
+        else
+            fold_kernel<double><<<blocks, 128, 0, st>>>(t->base, (const double *)t->W, t->nrows, t->S, (int)t->ncols, bf, (double *)wf);
+        bptr_kernel<<<(unsigned)((t->ncols + t->S + 255) / 256), 256, 0, st>>>(bf, t->nrows, t->S, (int)t->ncols, bp);
+        count_launch(2);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cudaFree(wf);
+        cudaFree(bf);
+        cudaFree(bp);
+        set_error("fold kernel failed: %s", cudaGetErrorString(e));
+        return LI_ERR_CUDA;
+    }
+    t->Wfold = wf;
+    t->bfold = bf;
+    t->bpf = bp;
+    return LI_OK;
+}
+
 static int reduce_to_host(cudaStream_t st, int init, int *result,
                           const std::function<void(int *)> &launch)
 {
@@ -427,6 +478,30 @@ int table_adj_rows(const li_table *t, int G, cudaStream_t st, int *rows)
     if (rc != LI_OK) return rc;
     std::lock_guard<std::mutex> lock(t->mu);
     t->adj_rows[G] = v;
+    *rows = v;
+    return LI_OK;
+}
+
+int table_adjf_rows(const li_table *t, int G, cudaStream_t st, int *rows)
+{
+    {
+        std::lock_guard<std::mutex> lock(t->mu);
+        auto it = t->adjf_rows.find(G);
+        if (it != t->adjf_rows.end()) {
+            *rows = it->second;
+            return LI_OK;
+        }
+    }
+    int rc = table_ensure_fold(t, st);
+    if (rc != LI_OK) return rc;
+    int v = 0;
+    const int ntiles = (int)((t->ncols + G - 1) / G);
+    rc = reduce_to_host(st, 0, &v, [&](int *d) {
+        adj_rows_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(t->bpf, t->S, (int)t->ncols, G, d);
+    });
+    if (rc != LI_OK) return rc;
+    std::lock_guard<std::mutex> lock(t->mu);
+    t->adjf_rows[G] = v;
     *rows = v;
     return LI_OK;
 }
@@ -553,6 +628,9 @@ int li_table_destroy(li_table *t)
     cudaFree(t->colptr);
     cudaFree(t->tent);
     cudaFree(t->rowstart);
+    cudaFree(t->Wfold);
+    cudaFree(t->bfold);
+    cudaFree(t->bpf);
     delete t;
     return LI_OK;
 }
