@@ -170,6 +170,14 @@ LI_API int li_sep_apply(int adjoint, int ndim, const li_table *const *tabs, cons
                  int64_t nbatch, double alpha, const void *src_dev, double beta, void *dst_dev,
                  void *workspace_dev, size_t workspace_bytes, int variant, void *stream);
 
+/* n independent separable applies in one call (one launch sequence, no per-call host overhead): apply k uses
+ * tabs[k*ndim .. k*ndim+ndim-1], src_dev[k] and dst_dev[k].  Several applies may share one dst (beta = 1): they are
+ * executed in order on `stream`, which is how `m = sum_k A_k' y_k` of iterative fitting (README: "A'*y") is
+ * accumulated.  Intermediate workspace, if any apply needs it, is managed by the library. */
+LI_API int li_sep_apply_batch(int adjoint, int ndim, int64_t n, const li_table *const *tabs, const int64_t *dims_other,
+                              int64_t nbatch, double alpha, const void *const *src_dev, double beta,
+                              void *const *dst_dev, int variant, void *stream);
+
 /* ---- operators with on-the-fly coefficients --------------------------------
  * 1-D: apply!(alpha, P, ker, x, src, beta, dst), src/unidimensional.jl:95-245.
  * Direct: src[len] -> dst[n]; Adjoint: src[n] -> dst[len].  x_dev: n positions of type T.

@@ -16,7 +16,7 @@ from .kernels import (Boundaries, CardinalCubicSpline, CatmullRomSpline, CubicSp
 from .mapping import (Adjoint, AdjointMapping, Composition, Direct, Gram, LinearMapping, Mapping, Operations,
                       Table, apply, apply_, apply_b, vcreate, vdot)
 from .nonseparable import AffineTransform2D, TwoDimensionalTransformInterpolator, affine_apply, intercept, rotate
-from .separable import sep2d_otf_apply, sep_apply_tables
+from .separable import sep2d_otf_apply, sep_apply_batch, sep_apply_tables
 from .sparse import Range, SparseInterpolator, SparseUnidimensionalInterpolator, fractional_index
 from .tabulated import TabulatedInterpolator, coefficients, columns, ncols, nrows, width
 from .unidimensional import otf1d_apply

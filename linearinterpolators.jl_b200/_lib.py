@@ -92,6 +92,8 @@ _PROTOS = {
     "li_sep_workspace_bytes": (_int, [_int, _int, C.POINTER(_vp), C.POINTER(_i64), _i64, C.POINTER(_sz)]),
     "li_sep_apply": (_int, [_int, _int, C.POINTER(_vp), C.POINTER(_i64), _i64, _dbl, _vp, _dbl, _vp, _vp, _sz,
                             _int, _vp]),
+    "li_sep_apply_batch": (_int, [_int, _int, _i64, C.POINTER(_vp), C.POINTER(_i64), _i64, _dbl, C.POINTER(_vp), _dbl,
+                                  C.POINTER(_vp), _int, _vp]),
     "li_otf1d_apply": (_int, [_int, _kd, _vp, _i64, _i64, _dbl, _vp, _dbl, _vp, _int, _vp]),
     "li_sep2d_otf_apply": (_int, [_int, _kd, _vp, _i64, _kd, _vp, _i64, _i64, _i64, _i64, _dbl, _vp, _dbl, _vp,
                                   _vp]),

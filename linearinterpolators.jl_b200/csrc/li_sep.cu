@@ -158,6 +158,39 @@ int li_sep_apply(int adjoint, int ndim, const li_table *const *tabs, const int64
                               workspace_bytes, variant, li::as_stream(stream));
 }
 
+int li_sep_apply_batch(int adjoint, int ndim, int64_t n, const li_table *const *tabs, const int64_t *dims_other,
+                       int64_t nbatch, double alpha, const void *const *src_dev, double beta, void *const *dst_dev,
+                       int variant, void *stream)
+{
+    LI_REQUIRE(n >= 0 && tabs && (n == 0 || (src_dev && dst_dev)), LI_ERR_ARG, "null argument");
+    cudaStream_t st = li::as_stream(stream);
+    for (int64_t k = 0; k < n; ++k) {
+        const li_table *const *tk = tabs + k * ndim;
+        size_t need = 0;
+        int rc = li_sep_workspace_bytes(adjoint, ndim, tk, dims_other, nbatch, &need);
+        if (rc != LI_OK) return rc;
+        void *ws = nullptr;
+        // (the fused 2-D kernels need no workspace; this buffer is only touched by the multi-pass fallback)
+        if (need && !(ndim == 2 && tk[0] && tk[1] && li::sep2d_fused_supported(tk[0], tk[1]))) {
+            rc = li::staging(2, need, &ws);
+            if (rc != LI_OK) return rc;
+        } else {
+            need = 0;
+        }
+        rc = li::sep_apply_impl(adjoint, ndim, tk, dims_other, nbatch, alpha, src_dev[k], beta, dst_dev[k], ws, need,
+                                variant, st);
+        if (rc == LI_ERR_ARG && need == 0) {   // the fused kernel declined: retry with a workspace
+            rc = li_sep_workspace_bytes(adjoint, ndim, tk, dims_other, nbatch, &need);
+            if (rc == LI_OK) rc = li::staging(2, need, &ws);
+            if (rc == LI_OK)
+                rc = li::sep_apply_impl(adjoint, ndim, tk, dims_other, nbatch, alpha, src_dev[k], beta, dst_dev[k], ws,
+                                        need, variant, st);
+        }
+        if (rc != LI_OK) return rc;
+    }
+    return LI_OK;
+}
+
 int li_sep_apply_host(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other, int64_t nbatch,
                       double alpha, const void *src_host, double beta, void *dst_host, int variant, void *stream)
 {

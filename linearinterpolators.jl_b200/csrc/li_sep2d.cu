@@ -639,7 +639,7 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     a.W2f = (const T *)t2->Wfold;
     // widest dst tile whose contributing src columns fit the staged width
     int TD1 = 0;
-    const int cands[] = {128, 120, 112, 96, 80, 64, 56, 48, 32, 24, 16, 8};
+    const int cands[] = {248, 240, 224, 208, 192, 176, 160, 144, 128, 120, 112, 96, 80, 64, 56, 48, 32, 24, 16, 8};
     for (int c : cands) {
         int rows = 0;
         rc = table_adj_rows(t1, c, st, &rows);

@@ -62,6 +62,36 @@ def sep_apply_tables(adjoint: bool, tabs, alpha, x, beta, y, owner=None, nbatch_
     return y
 
 
+def sep_apply_batch(adjoint: bool, tabs_list, alpha, srcs, beta, dsts, variant=_lib.VARIANT_AUTO):
+    """Many separable applies in ONE library call (`li_sep_apply_batch`): apply k uses the per-dimension tables
+    ``tabs_list[k]``, ``srcs[k]`` and ``dsts[k]`` (device arrays).  Entries of ``dsts`` may be the same array: with
+    ``beta = 1`` the applies accumulate in order, e.g. ``m += A_k' y_k`` over the frames of iterative fitting."""
+    n = len(tabs_list)
+    if n == 0:
+        return dsts
+    ndim = len(tabs_list[0])
+    dtype = tabs_list[0][0].dtype
+    handles = (C.c_void_p * (n * ndim))()
+    sp, dp = (C.c_void_p * n)(), (C.c_void_p * n)()
+    for k, (tabs, x, y) in enumerate(zip(tabs_list, srcs, dsts)):
+        if len(tabs) != ndim or any(t is None for t in tabs):
+            raise _lib.ErrorException("every apply needs one table per dimension")
+        if not (ar.is_device(x) and ar.is_device(y)):
+            raise _lib.ErrorException("sep_apply_batch works on device arrays")
+        x = ar.to_colmajor(x, dtype)
+        xin = tuple((t.nrows if adjoint else t.ncols) for t in tabs)
+        yout = tuple((t.ncols if adjoint else t.nrows) for t in tabs)
+        if ar.shape_of(x) != xin:
+            raise _lib.DimensionMismatch(f"source {k} has size {ar.shape_of(x)}, expected {xin}")
+        check_dst(y, yout, dtype)
+        for d, t in enumerate(tabs):
+            handles[k * ndim + d] = t.handle
+        sp[k], dp[k] = ar.data_ptr(x), ar.data_ptr(y)
+    _lib.check(_lib.lib.li_sep_apply_batch(int(adjoint), ndim, n, handles, None, 1, float(alpha), sp, float(beta), dp,
+                                           variant, ar.current_stream(dsts[0])))
+    return dsts
+
+
 def sep2d_otf_apply(alpha, P, ker1, x1, ker2, x2, src, beta, dst):
     """src/separable.jl:56-162.  Coefficients are evaluated on the device for this call only."""
     T = ker1.T

@@ -480,3 +480,26 @@ def test_separable_3d_passes(li):
     for d in (0, 1, 2):
         refa = O.tab_adjoint(JW[d][0], JW[d][1], m[d], d + 1, refa)
     assert_close(li.to_host(H.adj * li.to_device(y)), refa, T, factor=64)
+
+
+def test_sep_apply_batch_accumulates_frames(li):
+    # m = sum_k A_k' y_k in one library call (config #5 in small)
+    T = np.float32
+    rng = np.random.default_rng(55)
+    m, nframes = 72, 5
+    ker, okd = li.SafeFlat(li.LanczosKernel(T, 6)), O.kernel(O.LANCZOS, 6, O.SAFEFLAT)
+    xs = np.arange(1, m + 1, dtype=np.float64)
+    frames = np.asfortranarray(rng.standard_normal((m, m, nframes)).astype(T))
+    dfr = li.to_device(frames)
+    tabs, want = [], np.zeros((m, m))
+    for k in range(nframes):
+        d1, d2 = rng.uniform(-8, 8, 2)
+        A1, A2 = li.TabulatedInterpolator(T, 1, ker, xs + d1, m), li.TabulatedInterpolator(T, 2, ker, xs + d2, m)
+        tabs.append([A1.table, A2.table])
+        J1, W1 = O.maketable(okd, (xs + d1).astype(T), m, T)
+        J2, W2 = O.maketable(okd, (xs + d2).astype(T), m, T)
+        want += O.tab_adjoint(J2, W2, m, 2, O.tab_adjoint(J1, W1, m, 1, np.asfortranarray(frames[:, :, k])))
+    acc = li.device_empty((m, m), T)
+    acc.zero_()
+    li.sep_apply_batch(True, tabs, 1, [dfr[:, :, k] for k in range(nframes)], 1, [acc] * nframes)
+    assert_close(li.to_host(acc), want, T, factor=64)
