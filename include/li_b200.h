@@ -118,6 +118,8 @@ LI_API int li_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void
 LI_API int li_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
 LI_API int li_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes, void *stream);
 LI_API int li_memset_zero(void *dst_dev, size_t bytes, void *stream);
+LI_API int li_stream_create(void **stream);  /* a non-blocking cudaStream_t, for callers without a CUDA binding */
+LI_API int li_stream_destroy(void *stream);
 LI_API int li_stream_sync(void *stream);
 /* vscale!(y, beta) of LazyAlgebra (call sites src/tabulated.jl:353,386,
  * src/sparse.jl:211,255,656,699, ...): beta == 0 fills zeros without reading. */
@@ -212,6 +214,15 @@ LI_API int li_tab_apply_host(int adjoint, const li_table *t, int64_t npre, int64
 LI_API int li_sep_apply_host(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other,
                       int64_t nbatch, double alpha, const void *src_host, double beta,
                       void *dst_host, int variant, void *stream);
+
+/* Asynchronous variants: enqueue H2D copy, kernels and D2H copy on `stream` and return; the host buffers must be
+ * page-locked (li_host_alloc) and stay valid until li_stream_sync(stream).  Device staging buffers are kept per
+ * stream, so calls on different streams overlap (e.g. the D2H of a forward with the H2D of an adjoint). */
+LI_API int li_tab_apply_host_async(int adjoint, const li_table *t, int64_t npre, int64_t npost, double alpha,
+                                   const void *src_host, double beta, void *dst_host, int variant, void *stream);
+LI_API int li_sep_apply_host_async(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other,
+                                   int64_t nbatch, double alpha, const void *src_host, double beta,
+                                   void *dst_host, int variant, void *stream);
 
 /* ---- counters --------------------------------------------------------------
  * Number of CUDA kernels this library has launched in this process (all entry

@@ -7,7 +7,7 @@ module ``li_b200.py`` at the repository root.  Everything numerical happens in `
 not been built -- there is no CPU fallback.
 """
 from . import _lib
-from ._arrays import DeviceArray, device_empty, pinned_empty, to_device, to_host
+from ._arrays import DeviceArray, HostStream, async_host, device_empty, pinned_empty, to_device, to_host
 from ._lib import (ArgumentError, CudaError, DimensionMismatch, ErrorException, InexactError, LIB_PATH,
                    VARIANT_ATOMIC, VARIANT_AUTO, VARIANT_GATHER, launch_count)
 from .kernels import (Boundaries, CardinalCubicSpline, CatmullRomSpline, CubicSpline, Flat, Kernel, KeysSpline,

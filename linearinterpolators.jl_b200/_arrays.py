@@ -204,3 +204,49 @@ def to_host(x) -> np.ndarray:
             return np.asfortranarray(x.detach().permute(*reversed(range(x.ndim))).contiguous().cpu().numpy().T)
         return x.detach().cpu().numpy()
     return np.asarray(x)
+
+
+# ---- asynchronous host-staged calls -------------------------------------------------------------------------
+class HostStream:
+    """A CUDA stream for host-staged (numpy) applies.  Inside ``with async_host(stream):`` every apply on host
+    arrays only *enqueues* its H2D copy, kernels and D2H copy on that stream and returns; the arrays must be pinned
+    (:func:`pinned_empty`) and must not be touched before :meth:`synchronize`.  Applies issued on different streams
+    overlap, e.g. the download of a forward result with the upload of an adjoint's input."""
+
+    def __init__(self):
+        p = C.c_void_p()
+        _lib.check(_lib.lib.li_stream_create(C.byref(p)))
+        self.handle = p.value
+
+    def synchronize(self):
+        _lib.check(_lib.lib.li_stream_sync(self.handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib.li_stream_destroy(self.handle)
+                self.handle = None
+        except Exception:  # pragma: no cover
+            pass
+
+
+import contextlib
+import threading
+
+_tls = threading.local()
+
+
+def host_stream_state():
+    """(stream handle, asynchronous?) used by host-staged applies on this thread."""
+    st = getattr(_tls, "stream", None)
+    return (st.handle, True) if st is not None else (0, False)
+
+
+@contextlib.contextmanager
+def async_host(stream: HostStream):
+    prev = getattr(_tls, "stream", None)
+    _tls.stream = stream
+    try:
+        yield stream
+    finally:
+        _tls.stream = prev

@@ -81,6 +81,8 @@ _PROTOS = {
     "li_memcpy_d2h": (_int, [_vp, _vp, _sz, _vp]),
     "li_memcpy_d2d": (_int, [_vp, _vp, _sz, _vp]),
     "li_memset_zero": (_int, [_vp, _sz, _vp]),
+    "li_stream_create": (_int, [C.POINTER(_vp)]),
+    "li_stream_destroy": (_int, [_vp]),
     "li_stream_sync": (_int, [_vp]),
     "li_vscale": (_int, [_int, _vp, _i64, _dbl, _vp]),
     "li_table_create": (_int, [_kd, _vp, _int, _i64, _i64, _vp, C.POINTER(_vp)]),
@@ -102,6 +104,9 @@ _PROTOS = {
     "li_tab_apply_host": (_int, [_int, _vp, _i64, _i64, _dbl, _vp, _dbl, _vp, _int, _vp]),
     "li_sep_apply_host": (_int, [_int, _int, C.POINTER(_vp), C.POINTER(_i64), _i64, _dbl, _vp, _dbl, _vp, _int,
                                  _vp]),
+    "li_tab_apply_host_async": (_int, [_int, _vp, _i64, _i64, _dbl, _vp, _dbl, _vp, _int, _vp]),
+    "li_sep_apply_host_async": (_int, [_int, _int, C.POINTER(_vp), C.POINTER(_i64), _i64, _dbl, _vp, _dbl, _vp, _int,
+                                       _vp]),
     "li_kernel_launch_count": (_i64, []),
 }
 for _name, (_res, _args) in _PROTOS.items():

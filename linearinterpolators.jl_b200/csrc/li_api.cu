@@ -41,22 +41,30 @@ int vscale_impl(int dtype, void *y, int64_t n, double beta, cudaStream_t st)
     return LI_OK;
 }
 
-// Grow-only device staging buffers for the host-buffer entry points (one set per host thread):
-// cudaMalloc/cudaFree per call would dominate small applies and serialise the device.
-static thread_local void *g_stage[3] = {nullptr, nullptr, nullptr};
-static thread_local size_t g_stage_bytes[3] = {0, 0, 0};
+// Grow-only device staging buffers for the host-buffer entry points, one set per (host thread, stream):
+// cudaMalloc/cudaFree per call would dominate small applies and serialise the device, and calls on different
+// streams must not share buffers.
+struct StageSet {
+    void *ptr[3] = {nullptr, nullptr, nullptr};
+    size_t bytes[3] = {0, 0, 0};
+};
+static thread_local std::map<void *, StageSet> g_stage;
 
-int staging(int slot, size_t bytes, void **out)
+int staging(int slot, size_t bytes, void **out, void *stream_key)
 {
-    if (bytes > g_stage_bytes[slot]) {
-        if (g_stage[slot]) cudaFree(g_stage[slot]);
-        g_stage[slot] = nullptr;
-        g_stage_bytes[slot] = 0;
+    StageSet &s = g_stage[stream_key];
+    if (bytes > s.bytes[slot]) {
+        if (s.ptr[slot]) {
+            cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream_key));   // nothing in flight may still use it
+            cudaFree(s.ptr[slot]);
+        }
+        s.ptr[slot] = nullptr;
+        s.bytes[slot] = 0;
         const size_t want = bytes + bytes / 8 + 256;
-        LI_CUDA(cudaMalloc(&g_stage[slot], want));
-        g_stage_bytes[slot] = want;
+        LI_CUDA(cudaMalloc(&s.ptr[slot], want));
+        s.bytes[slot] = want;
     }
-    *out = g_stage[slot];
+    *out = s.ptr[slot];
     return LI_OK;
 }
 
@@ -159,6 +167,21 @@ int li_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes, void *stream
 int li_memset_zero(void *dst_dev, size_t bytes, void *stream)
 {
     LI_CUDA(cudaMemsetAsync(dst_dev, 0, bytes, li::as_stream(stream)));
+    return LI_OK;
+}
+
+int li_stream_create(void **stream)
+{
+    LI_REQUIRE(stream, LI_ERR_ARG, "null argument");
+    cudaStream_t st;
+    LI_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *stream = st;
+    return LI_OK;
+}
+
+int li_stream_destroy(void *stream)
+{
+    LI_CUDA(cudaStreamDestroy(li::as_stream(stream)));
     return LI_OK;
 }
 

@@ -92,7 +92,7 @@ int table_create_impl(const li_kernel_desc *ker, const void *pos_dev, int64_t nr
 int tab_apply_impl(int adjoint, const li_table *t, int64_t npre, int64_t npost, double alpha,
                    const void *src, double beta, void *dst, int variant, cudaStream_t st);
 int vscale_impl(int dtype, void *y, int64_t n, double beta, cudaStream_t st);
-int staging(int slot, size_t bytes, void **out);  // grow-only per-thread device scratch (slots 0..2)
+int staging(int slot, size_t bytes, void **out, void *stream_key = nullptr);  // grow-only device scratch per (thread, stream)
 int sep2d_fused_supported(const li_table *t1, const li_table *t2);
 int sep2d_fused_apply(int adjoint, const li_table *t1, const li_table *t2, int64_t nbatch,
                       double alpha, const void *src, double beta, void *dst, cudaStream_t st,

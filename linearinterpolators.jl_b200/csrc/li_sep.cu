@@ -172,7 +172,7 @@ int li_sep_apply_batch(int adjoint, int ndim, int64_t n, const li_table *const *
         void *ws = nullptr;
         // (the fused 2-D kernels need no workspace; this buffer is only touched by the multi-pass fallback)
         if (need && !(ndim == 2 && tk[0] && tk[1] && li::sep2d_fused_supported(tk[0], tk[1]))) {
-            rc = li::staging(2, need, &ws);
+            rc = li::staging(2, need, &ws, stream);
             if (rc != LI_OK) return rc;
         } else {
             need = 0;
@@ -181,7 +181,7 @@ int li_sep_apply_batch(int adjoint, int ndim, int64_t n, const li_table *const *
                                 variant, st);
         if (rc == LI_ERR_ARG && need == 0) {   // the fused kernel declined: retry with a workspace
             rc = li_sep_workspace_bytes(adjoint, ndim, tk, dims_other, nbatch, &need);
-            if (rc == LI_OK) rc = li::staging(2, need, &ws);
+            if (rc == LI_OK) rc = li::staging(2, need, &ws, stream);
             if (rc == LI_OK)
                 rc = li::sep_apply_impl(adjoint, ndim, tk, dims_other, nbatch, alpha, src_dev[k], beta, dst_dev[k], ws,
                                         need, variant, st);
@@ -191,8 +191,11 @@ int li_sep_apply_batch(int adjoint, int ndim, int64_t n, const li_table *const *
     return LI_OK;
 }
 
-int li_sep_apply_host(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other, int64_t nbatch,
-                      double alpha, const void *src_host, double beta, void *dst_host, int variant, void *stream)
+}  // extern "C"
+
+static int sep_apply_host_impl(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other,
+                               int64_t nbatch, double alpha, const void *src_host, double beta, void *dst_host,
+                               int variant, void *stream, bool sync)
 {
     LI_REQUIRE(src_host && dst_host, LI_ERR_ARG, "null argument");
     cudaStream_t st = li::as_stream(stream);
@@ -207,22 +210,46 @@ int li_sep_apply_host(int adjoint, int ndim, const li_table *const *tabs, const 
     const size_t nin = (size_t)plan.in_elems * es, nout = (size_t)plan.out_elems[plan.npass - 1] * es;
     size_t wsb = 0, half = 0;
     li::sep_workspace(plan, dtype, &wsb, &half);
+    if (ndim == 2 && tabs[0] && tabs[1] && li::sep2d_fused_supported(tabs[0], tabs[1]) && variant != LI_VARIANT_ATOMIC)
+        wsb = 0;   // the fused kernel needs none; if it declines the call below retries with a workspace
     void *dsrc = nullptr, *ddst = nullptr, *ws = nullptr;
-    rc = li::staging(0, nin ? nin : 1, &dsrc);
-    if (rc == LI_OK) rc = li::staging(1, nout ? nout : 1, &ddst);
-    if (rc == LI_OK && wsb) rc = li::staging(2, wsb, &ws);
+    rc = li::staging(0, nin ? nin : 1, &dsrc, stream);
+    if (rc == LI_OK) rc = li::staging(1, nout ? nout : 1, &ddst, stream);
+    if (rc == LI_OK && wsb) rc = li::staging(2, wsb, &ws, stream);
     if (rc != LI_OK) return rc;
     cudaError_t e = cudaMemcpyAsync(dsrc, src_host, nin, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && beta != 0.0) e = cudaMemcpyAsync(ddst, dst_host, nout, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess)
+    if (e == cudaSuccess) {
         rc = li::sep_apply_impl(adjoint, ndim, tabs, dims_other, nbatch, alpha, dsrc, beta, ddst, ws, wsb, variant, st);
+        if (rc == LI_ERR_ARG && wsb == 0) {   // fused kernel declined
+            li::sep_workspace(plan, dtype, &wsb, &half);
+            rc = li::staging(2, wsb, &ws, stream);
+            if (rc == LI_OK)
+                rc = li::sep_apply_impl(adjoint, ndim, tabs, dims_other, nbatch, alpha, dsrc, beta, ddst, ws, wsb, variant, st);
+        }
+    }
     if (e == cudaSuccess && rc == LI_OK) e = cudaMemcpyAsync(dst_host, ddst, nout, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && sync) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         li::set_error("host-staged separable apply failed: %s", cudaGetErrorString(e));
         return LI_ERR_CUDA;
     }
     return rc;
+}
+
+extern "C" {
+
+int li_sep_apply_host(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other, int64_t nbatch,
+                      double alpha, const void *src_host, double beta, void *dst_host, int variant, void *stream)
+{
+    return sep_apply_host_impl(adjoint, ndim, tabs, dims_other, nbatch, alpha, src_host, beta, dst_host, variant, stream, true);
+}
+
+int li_sep_apply_host_async(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other,
+                            int64_t nbatch, double alpha, const void *src_host, double beta, void *dst_host,
+                            int variant, void *stream)
+{
+    return sep_apply_host_impl(adjoint, ndim, tabs, dims_other, nbatch, alpha, src_host, beta, dst_host, variant, stream, false);
 }
 
 // 1-D on-the-fly: coefficients are generated on the device for this call only.

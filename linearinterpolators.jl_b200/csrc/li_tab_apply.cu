@@ -259,8 +259,10 @@ int li_tab_apply(int adjoint, const li_table *t, int64_t npre, int64_t npost, do
     return li::tab_apply_impl(adjoint, t, npre, npost, alpha, src_dev, beta, dst_dev, variant, li::as_stream(stream));
 }
 
-int li_tab_apply_host(int adjoint, const li_table *t, int64_t npre, int64_t npost, double alpha,
-                      const void *src_host, double beta, void *dst_host, int variant, void *stream)
+}  // extern "C"
+
+static int tab_apply_host_impl(int adjoint, const li_table *t, int64_t npre, int64_t npost, double alpha,
+                               const void *src_host, double beta, void *dst_host, int variant, void *stream, bool sync)
 {
     LI_REQUIRE(t && src_host && dst_host, LI_ERR_ARG, "null argument");
     cudaStream_t st = li::as_stream(stream);
@@ -268,19 +270,33 @@ int li_tab_apply_host(int adjoint, const li_table *t, int64_t npre, int64_t npos
     const size_t nin = (size_t)(npre * npost * (adjoint ? t->nrows : t->ncols)) * es;
     const size_t nout = (size_t)(npre * npost * (adjoint ? t->ncols : t->nrows)) * es;
     void *dsrc = nullptr, *ddst = nullptr;
-    int rc = li::staging(0, nin ? nin : 1, &dsrc);
-    if (rc == LI_OK) rc = li::staging(1, nout ? nout : 1, &ddst);
+    int rc = li::staging(0, nin ? nin : 1, &dsrc, stream);
+    if (rc == LI_OK) rc = li::staging(1, nout ? nout : 1, &ddst, stream);
     if (rc != LI_OK) return rc;
     cudaError_t e = cudaMemcpyAsync(dsrc, src_host, nin, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && beta != 0.0) e = cudaMemcpyAsync(ddst, dst_host, nout, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) rc = li::tab_apply_impl(adjoint, t, npre, npost, alpha, dsrc, beta, ddst, variant, st);
     if (e == cudaSuccess && rc == LI_OK) e = cudaMemcpyAsync(dst_host, ddst, nout, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && sync) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         li::set_error("host-staged apply failed: %s", cudaGetErrorString(e));
         return LI_ERR_CUDA;
     }
     return rc;
+}
+
+extern "C" {
+
+int li_tab_apply_host(int adjoint, const li_table *t, int64_t npre, int64_t npost, double alpha,
+                      const void *src_host, double beta, void *dst_host, int variant, void *stream)
+{
+    return tab_apply_host_impl(adjoint, t, npre, npost, alpha, src_host, beta, dst_host, variant, stream, true);
+}
+
+int li_tab_apply_host_async(int adjoint, const li_table *t, int64_t npre, int64_t npost, double alpha,
+                            const void *src_host, double beta, void *dst_host, int variant, void *stream)
+{
+    return tab_apply_host_impl(adjoint, t, npre, npost, alpha, src_host, beta, dst_host, variant, stream, false);
 }
 
 }  // extern "C"

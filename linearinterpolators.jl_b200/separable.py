@@ -57,8 +57,10 @@ def sep_apply_tables(adjoint: bool, tabs, alpha, x, beta, y, owner=None, nbatch_
                                          float(beta), ar.data_ptr(y), ar.data_ptr(ws) if ws is not None else None,
                                          wsb, variant, ar.current_stream(y)))
     else:
-        _lib.check(_lib.lib.li_sep_apply_host(int(adjoint), n, handles, other, nbatch, float(alpha), ar.data_ptr(x),
-                                              float(beta), ar.data_ptr(y), variant, 0))
+        stream, asynchronous = ar.host_stream_state()
+        fn = _lib.lib.li_sep_apply_host_async if asynchronous else _lib.lib.li_sep_apply_host
+        _lib.check(fn(int(adjoint), n, handles, other, nbatch, float(alpha), ar.data_ptr(x), float(beta),
+                      ar.data_ptr(y), variant, stream))
     return y
 
 

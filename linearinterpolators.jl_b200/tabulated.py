@@ -21,8 +21,10 @@ def run_tab(table: Table, adjoint: bool, npre: int, npost: int, alpha, src, beta
         _lib.check(_lib.lib.li_tab_apply(int(adjoint), table.handle, npre, npost, float(alpha), ar.data_ptr(src),
                                          float(beta), ar.data_ptr(dst), variant, ar.current_stream(dst)))
     else:
-        _lib.check(_lib.lib.li_tab_apply_host(int(adjoint), table.handle, npre, npost, float(alpha), ar.data_ptr(src),
-                                              float(beta), ar.data_ptr(dst), variant, 0))
+        stream, asynchronous = ar.host_stream_state()
+        fn = _lib.lib.li_tab_apply_host_async if asynchronous else _lib.lib.li_tab_apply_host
+        _lib.check(fn(int(adjoint), table.handle, npre, npost, float(alpha), ar.data_ptr(src), float(beta),
+                      ar.data_ptr(dst), variant, stream))
     return dst
 
 

@@ -503,3 +503,30 @@ def test_sep_apply_batch_accumulates_frames(li):
     acc.zero_()
     li.sep_apply_batch(True, tabs, 1, [dfr[:, :, k] for k in range(nframes)], 1, [acc] * nframes)
     assert_close(li.to_host(acc), want, T, factor=64)
+
+
+def test_async_host_streams(li):
+    # host-staged applies enqueued on two streams overlap and give the same results as the blocking calls
+    T = np.float32
+    rng = np.random.default_rng(3)
+    m, n = 200, 400
+    x = np.linspace(1, m, n)
+    ker = li.LanczosKernel(T, 4)
+    H = li.TabulatedInterpolator(T, 1, ker, x, m) * li.TabulatedInterpolator(T, 2, ker, x, m)
+    src = li.pinned_empty((m, m), T)
+    src[...] = rng.standard_normal((m, m))
+    yin = li.pinned_empty((n, n), T)
+    yin[...] = rng.standard_normal((n, n))
+    out, back = li.vcreate(li.Direct, H, src), li.vcreate(li.Adjoint, H, yin)
+    ref_out, ref_back = H * np.asarray(src), H.adj * np.asarray(yin)
+    sa, sb = li.HostStream(), li.HostStream()
+    for _ in range(3):
+        out[...] = 0
+        back[...] = 0
+        with li.async_host(sa):
+            li.apply_b(1, li.Direct, H, src, False, 0, out)
+        with li.async_host(sb):
+            li.apply_b(1, li.Adjoint, H, yin, False, 0, back)
+        sa.synchronize()
+        sb.synchronize()
+        assert np.array_equal(np.asarray(out), ref_out) and np.array_equal(np.asarray(back), ref_back)
