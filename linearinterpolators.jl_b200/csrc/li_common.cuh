@@ -72,6 +72,10 @@ struct li_table {
     mutable void *Wfold = nullptr;      // [nrows*S] folded weights
     mutable int32_t *bfold = nullptr;   // [nrows] folded window bases, in [0, ncols - S]
     mutable int32_t *bpf = nullptr;     // bptr table over bfold, [ncols + S]
+    mutable int32_t *irrp = nullptr;    // [ncols+1] prefix count of dst rows fed by a number of src rows != reg_R
+    mutable int reg_R = 0;              // the regular number of src rows per dst row (1 or 2), 0 if none
+    // per tile height: device list of tile rows, regular ones first; second = number of regular tile rows
+    mutable std::map<int, std::pair<int32_t *, int>> tile_rows;
     mutable std::map<int, int> adjf_rows;
     // cached footprint bounds: key = tile rows G -> max over aligned tiles of (max base - min base)
     mutable std::map<int, int> fwd_span;
@@ -86,6 +90,9 @@ int table_fwd_span(const li_table *t, int G, cudaStream_t st, int *span);
 int table_adj_rows(const li_table *t, int G, cudaStream_t st, int *rows);
 int table_ensure_fold(const li_table *t, cudaStream_t st);            // needs ncols >= S
 int table_adjf_rows(const li_table *t, int G, cudaStream_t st, int *rows);  // like table_adj_rows, folded bases
+// tile rows of height TD2 over the columns of t, regular ones (all dst rows fed by exactly reg_R rows, none clamped)
+// first: *list (device) has ntiles entries, the first *nregular of them regular
+int table_tile_rows(const li_table *t, int TD2, cudaStream_t st, const int32_t **list, int *nregular);
 // builds a table from device positions into preallocated device arrays (used by the OTF operators)
 int table_create_impl(const li_kernel_desc *ker, const void *pos_dev, int64_t nrows, int64_t ncols,
                       cudaStream_t st, li_table **out);

@@ -77,6 +77,7 @@ struct SepArgs {
     const T *W1, *W2;              // [n*S]
     const int32_t *bp1, *bp2;      // adjoint only: bptr tables (see li_table.cu), [m+S]; bp2 is over FOLDED bases
     const T *W2f;                  // adjoint only: folded dim-2 weights (li_table.cu: fold_kernel)
+    const int32_t *rowlist;        // adjoint only: tile rows handled by this launch (null: all, in order)
     int n1, n2;                    // "rows" side (fine grid for an upsampling operator)
     int m1, m2;                    // "columns" side
     int tiles1, tiles2;
@@ -389,7 +390,7 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1, const int R2 /* staged dim-2
     int bid = blockIdx.x;
     const int tile1 = bid % a.tiles1;
     bid /= a.tiles1;
-    const int tile2 = bid % a.tiles2;
+    const int tile2 = a.rowlist ? a.rowlist[bid % a.tiles2] : bid % a.tiles2;   // (a.tiles2 = tile rows of this launch)
     const int64_t batch = bid / a.tiles2;
     const int c0 = tile1 * TD1, c1 = min(c0 + TD1, a.m1);   // owned dst columns [c0, c1)
     const int d0 = tile2 * TD2, d1 = min(d0 + TD2, a.m2);   // owned dst rows    [d0, d1)
@@ -564,6 +565,171 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1, const int R2 /* staged dim-2
 }
 
 // ---------------------------------------------------------------------------------------------
+// Adjoint, statically scheduled kernel for REGULAR tile rows: full tile rows whose dst rows are each fed by exactly
+// R src rows with no clamped tap (the interior of a same-rate (R = 1) or 2x (R = 2) resampling; the host finds them
+// from the table, li_table.cu: table_tile_rows).  Same tiling, same phases and same summation order as the generic
+// kernel above, but phase 1 has no per-row control flow at all: row j of an unrolled block of NB rows belongs to dst
+// row v + j / R, the src rows are plain vector loads kept NB rows ahead in registers, and the only index lookups
+// (bptr entries, the dim-1 taps of phase 2) are issued in one batch at the start so the prologue costs one memory
+// round trip.  (A micro-benchmark of this data flow, scratch/mb/adj_v9.cu, runs config #2 in 85 us.)
+template <typename T, int S1, int S2, bool BETA, int R>
+__global__ void __launch_bounds__(ADJ_NT, (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : 2)
+sep2d_adj_regular_kernel(const SepArgs<T> a, const int TD1)
+{
+    constexpr int TD2 = ADJ_TD2, NT = ADJ_NT, NG = ADJ_NG, TPG = NT / NG, PT = 2 * TPG, RG = TD2 / NG;
+    constexpr int PH = PT / 2, PLANE = TD2 * PH + 16;
+    constexpr int NBM = (S2 * R >= 4) ? 1 : (4 + S2 * R - 1) / (S2 * R);
+    constexpr int NB = S2 * R * NBM;                         // rows per unrolled block == register queue depth
+    constexpr int NROW = R * (RG + S2 - 1);                  // src rows of a group
+    constexpr int CT = 128, NSL = NT / CT, RS = TD2 / NSL;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sT = reinterpret_cast<T *>(smem_raw);                 // [2][TD2][PH] (+skew)
+    T *sW2 = sT + 2 * PLANE;                                 // [NG][NROW][S2] folded dim-2 weights
+
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int tile1 = bid % a.tiles1;
+    bid /= a.tiles1;
+    const int tile2 = a.rowlist[bid % a.tiles2];
+    const int64_t batch = bid / a.tiles2;
+    const int c0 = tile1 * TD1, c1 = min(c0 + TD1, a.m1);
+    const int d0 = tile2 * TD2;                              // (regular tile rows are full: d1 = d0 + TD2)
+    const T *src = a.src + batch * (int64_t)a.n1 * a.n2;
+    T *dst = a.dst + batch * (int64_t)a.m1 * a.m2;
+    const int g = tid / TPG, ct = tid % TPG;
+    const int ka = d0 + g * RG, kb = ka + RG, v0 = ka - (S2 - 1);
+
+    // round 1: every index lookup of the tile
+    const int r1lo_raw = a.bp1[c0], r1hi = a.bp1[c1 - 1 + S1];
+    const int i2lo = a.bp2[ka];
+    const int kc = tid % CT, sl = tid / CT;
+    const int k1a = min(c0 + kc, a.m1 - 1);
+    int pe0 = a.bp1[k1a], pe1 = a.bp1[k1a + S1];
+    const int r1lo = r1lo_raw & ~1, ncol = r1hi - r1lo;      // (launched on vector-aligned sources only)
+
+    // round 2: the first NB src rows of this thread's column pair, the dim-2 weights, the dim-1 taps
+    const bool have = 2 * ct < ncol;
+    const T *gp = src + (int64_t)i2lo * a.n1 + r1lo + 2 * ct;
+    const int64_t gstep = (int64_t)a.n1 * (int64_t)sizeof(T);
+    int togo = have ? NROW : 0;
+    auto load = [&]() {
+        Pack<T, 2> y;
+        y.v[0] = y.v[1] = (T)0;
+        if (togo > 0) y = ld_pack<T, 2>(gp);   // (the column after the last staged one is inside the row)
+        --togo;
+        gp = reinterpret_cast<const T *>(reinterpret_cast<const char *>(gp) + gstep);
+        return y;
+    };
+    Pack<T, 2> q[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) q[j] = load();
+    for (int k = ct; k < NROW * S2; k += TPG) sW2[g * NROW * S2 + k] = a.W2f[(int64_t)i2lo * S2 + k];
+    // dim-1 taps of dst column k1 (interior columns: one tap per contributing src column, straight from global --
+    // they are only needed in phase 2); edge columns and very long lists take the generic loop of phase 2
+    auto taps = [&](int k1, int e_first, int e_end, T (&tw)[ADJ_MAXE]) {
+        const bool interior = k1 > 0 && k1 < a.m1 - 1 && k1 < c1;
+        const int cnt = interior ? min(e_end - e_first, ADJ_MAXE) : 0;
+#pragma unroll
+        for (int k = 0; k < ADJ_MAXE; ++k) {
+            tw[k] = (T)0;
+            if (k < cnt) {
+                const int i1 = e_first + k;
+                tw[k] = a.W1[(int64_t)i1 * S1 + (k1 - a.base1[i1])];
+            }
+        }
+        return cnt;
+    };
+    T tw[ADJ_MAXE];
+    int cnt = taps(c0 + kc, pe0, pe1, tw);
+    __syncthreads();
+
+    // ---- phase 1: static schedule
+    {
+        T A0[S2], A1[S2];
+#pragma unroll
+        for (int s = 0; s < S2; ++s) A0[s] = A1[s] = (T)0;
+        const T *pw = sW2 + g * NROW * S2;
+        T *tp = sT + (ka - d0) * PH + ct;   // plane 0 (even staged columns); plane 1 at +PLANE
+        for (int v = v0; v < kb; v += NB / R) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int vv = v + j / R;
+                if (vv < kb) {   // (block-uniform) only the last block is partial
+                    const Pack<T, 2> y = q[j];
+                    q[j] = load();
+                    T w[S2];
+                    ld_weights<T, S2>(pw, w);
+                    pw += S2;
+#pragma unroll
+                    for (int s = 0; s < S2; ++s) {
+                        A0[(j / R + s) % S2] = fmaT(w[s], y.v[0], A0[(j / R + s) % S2]);
+                        A1[(j / R + s) % S2] = fmaT(w[s], y.v[1], A1[(j / R + s) % S2]);
+                    }
+                    if (j % R == R - 1) {   // dst row vv is complete
+                        if (vv >= ka) {
+                            tp[0] = A0[(j / R) % S2];
+                            tp[PLANE] = A1[(j / R) % S2];
+                            tp += PH;
+                        }
+                        A0[(j / R) % S2] = A1[(j / R) % S2] = (T)0;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: gather along dim 1
+    for (int kk0 = kc; kk0 < c1 - c0; kk0 += CT) {
+        const int k1 = c0 + kk0;
+        if (kk0 != kc) {   // TD1 > CT: further passes look their taps up now
+            pe0 = a.bp1[k1], pe1 = a.bp1[k1 + S1];
+            cnt = taps(k1, pe0, pe1, tw);
+        }
+        const int e0 = pe0 - r1lo, e1 = pe1 - r1lo;
+        const T *rowbase = sT + sl * RS * PH;
+        T acc[RS];
+#pragma unroll
+        for (int r = 0; r < RS; ++r) acc[r] = (T)0;
+        const int q0 = e0 & 1;
+        const T *pE = rowbase + q0 * PLANE + (e0 >> 1);
+        const T *pO = rowbase + (1 - q0) * PLANE + (e0 >> 1) + q0;
+#pragma unroll
+        for (int k = 0; k < ADJ_MAXE; ++k) {
+            if (k < cnt) {
+                const T *p = (k & 1) ? pO + (k - 1) / 2 : pE + k / 2;
+#pragma unroll
+                for (int r = 0; r < RS; ++r) acc[r] = fmaT(tw[k], p[r * PH], acc[r]);
+            }
+        }
+        for (int e = e0 + cnt; e < e1; ++e) {   // edge columns (clamped taps) and very long lists
+            const int b = a.base1[r1lo + e];
+            int slo = k1 - b, shi = k1 - b;   // taps s with clamp(b + s) == k1
+            if (k1 == 0) slo = 0;
+            if (k1 == a.m1 - 1) shi = S1 - 1;
+            slo = max(slo, 0);
+            shi = min(shi, S1 - 1);
+            const T *p = rowbase + (e & 1) * PLANE + (e >> 1);
+            for (int s = slo; s <= shi; ++s) {
+                const T ws = a.W1[(int64_t)(r1lo + e) * S1 + s];
+#pragma unroll
+                for (int r = 0; r < RS; ++r) acc[r] = fmaT(ws, p[r * PH], acc[r]);
+            }
+        }
+        T *d = dst + (int64_t)(d0 + sl * RS) * a.m1 + k1;
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            T *dr = d + (int64_t)r * a.m1;
+            if constexpr (BETA)
+                *dr = fmaT(a.beta, *dr, a.alpha * acc[r]);
+            else
+                *dr = a.alpha * acc[r];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 static const int kSmemLimit = 200 * 1024;
 
 template <typename KernT>
@@ -663,18 +829,48 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     if (smem > (size_t)kSmemLimit) return LI_OK;
     const int64_t blocks = (int64_t)a.tiles1 * a.tiles2 * nbatch;
     LI_REQUIRE(blocks <= 0x7fffffffLL, LI_ERR_UNSUPPORTED, "too many tiles");
-    if (a.beta != (T)0) {
-        auto kern = sep2d_adj_kernel<T, S1, S2, true>;
-        rc = set_smem(kern, smem);
-        if (rc != LI_OK) return rc;
-        kern<<<(unsigned)blocks, ADJ_NT, smem, st>>>(a, TD1, R2);
-    } else {
-        auto kern = sep2d_adj_kernel<T, S1, S2, false>;
-        rc = set_smem(kern, smem);
-        if (rc != LI_OK) return rc;
-        kern<<<(unsigned)blocks, ADJ_NT, smem, st>>>(a, TD1, R2);
+    // regular tile rows (li_table.cu: table_tile_rows) go to the statically scheduled kernel, the others (array
+    // edges, irregular rates) to the generic one: two launches over disjoint lists of tile rows
+    const int32_t *rowlist = nullptr;
+    int nreg = 0;
+    rc = table_tile_rows(t2, ADJ_TD2, st, &rowlist, &nreg);
+    if (rc != LI_OK) return rc;
+    const int R = t2->reg_R;
+    const bool vec4 = (a.n1 % 2 == 0) && (((uintptr_t)a.src) % (2 * sizeof(T)) == 0);
+    if ((R != 1 && R != 2) || !vec4) nreg = 0;
+    const int ntile_rows = a.tiles2;
+    const bool beta = a.beta != (T)0;
+    const size_t smem_reg = (2 * ((size_t)ADJ_TD2 * (PT / 2) + 16) + (size_t)NG * 2 * (RG + S2 - 1) * S2) * sizeof(T);
+#define LI_ADJ_REG(B, RR)                                                                     \
+    if (beta == B && R == RR && nreg > 0) {                                                   \
+        auto kern = sep2d_adj_regular_kernel<T, S1, S2, B, RR>;                               \
+        rc = set_smem(kern, smem_reg);                                                        \
+        if (rc != LI_OK) return rc;                                                           \
+        a.rowlist = rowlist;                                                                  \
+        a.tiles2 = nreg;                                                                      \
+        kern<<<(unsigned)((int64_t)a.tiles1 * nreg * nbatch), ADJ_NT, smem_reg, st>>>(a, TD1); \
+        count_launch();                                                                       \
     }
-    LI_CHECK_LAUNCH();
+    LI_ADJ_REG(false, 1) LI_ADJ_REG(false, 2) LI_ADJ_REG(true, 1) LI_ADJ_REG(true, 2)
+#undef LI_ADJ_REG
+    if (ntile_rows - nreg > 0) {
+        a.rowlist = rowlist + nreg;
+        a.tiles2 = ntile_rows - nreg;
+        const unsigned gblocks = (unsigned)((int64_t)a.tiles1 * a.tiles2 * nbatch);
+        if (beta) {
+            auto kern = sep2d_adj_kernel<T, S1, S2, true>;
+            rc = set_smem(kern, smem);
+            if (rc != LI_OK) return rc;
+            kern<<<gblocks, ADJ_NT, smem, st>>>(a, TD1, R2);
+        } else {
+            auto kern = sep2d_adj_kernel<T, S1, S2, false>;
+            rc = set_smem(kern, smem);
+            if (rc != LI_OK) return rc;
+            kern<<<gblocks, ADJ_NT, smem, st>>>(a, TD1, R2);
+        }
+        count_launch();
+    }
+    LI_CUDA(cudaGetLastError());
     *done = true;
     return LI_OK;
 }

@@ -6,6 +6,7 @@
 
 #include <climits>
 #include <functional>
+#include <vector>
 
 #include <cub/cub.cuh>
 
@@ -381,6 +382,14 @@ int table_ensure_rowstart(const li_table *t, cudaStream_t st)
     return LI_OK;
 }
 
+// irr[v] = 1 if the number of rows whose folded window starts at column v differs from R (inclusive prefix sums
+// are taken afterwards): tile rows with irr-free ranges take the statically scheduled adjoint kernel
+__global__ void irregular_kernel(const int32_t *__restrict__ bpf, int S, int ncols, int R, int32_t *__restrict__ irr)
+{
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < ncols) irr[v] = (bpf[v + S] - bpf[v + S - 1]) != R;
+}
+
 int table_ensure_fold(const li_table *t, cudaStream_t st)
 {
     std::lock_guard<std::mutex> lock(t->mu);
@@ -409,9 +418,35 @@ int table_ensure_fold(const li_table *t, cudaStream_t st)
         set_error("fold kernel failed: %s", cudaGetErrorString(e));
         return LI_ERR_CUDA;
     }
+    // regularity: R src rows per dst row (R = 1: same-rate resampling, R = 2: 2x up-sampling)
+    const int R = (int)((t->nrows + t->ncols / 2) / t->ncols);
+    int32_t *irr = nullptr, *irrp = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    if (R >= 1 && R <= 2) {
+        e = cudaMalloc(&irr, (size_t)t->ncols * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&irrp, (size_t)(t->ncols + 1) * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMemsetAsync(irrp, 0, sizeof(int32_t), st);
+        if (e == cudaSuccess) {
+            irregular_kernel<<<(unsigned)((t->ncols + 255) / 256), 256, 0, st>>>(bp, t->S, (int)t->ncols, R, irr);
+            count_launch();
+            e = cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, irr, irrp + 1, (int)t->ncols, st);
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes);
+        if (e == cudaSuccess) e = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, irr, irrp + 1, (int)t->ncols, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(irr);
+        cudaFree(tmp);
+        if (e != cudaSuccess) {
+            cudaFree(irrp);
+            irrp = nullptr;
+        }
+    }
     t->Wfold = wf;
     t->bfold = bf;
     t->bpf = bp;
+    t->irrp = irrp;
+    t->reg_R = irrp ? R : 0;
     return LI_OK;
 }
 
@@ -503,6 +538,43 @@ int table_adjf_rows(const li_table *t, int G, cudaStream_t st, int *rows)
     std::lock_guard<std::mutex> lock(t->mu);
     t->adjf_rows[G] = v;
     *rows = v;
+    return LI_OK;
+}
+
+int table_tile_rows(const li_table *t, int TD2, cudaStream_t st, const int32_t **list, int *nregular)
+{
+    int rc = table_ensure_fold(t, st);
+    if (rc != LI_OK) return rc;
+    std::lock_guard<std::mutex> lock(t->mu);
+    auto it = t->tile_rows.find(TD2);
+    if (it == t->tile_rows.end()) {
+        const int ntiles = (int)((t->ncols + TD2 - 1) / TD2);
+        std::vector<int32_t> irrp(t->ncols + 1, 0), order;
+        if (t->irrp) {
+            LI_CUDA(cudaMemcpyAsync(irrp.data(), t->irrp, (t->ncols + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            LI_CUDA(cudaStreamSynchronize(st));
+        }
+        std::vector<int32_t> irregular;
+        for (int k = 0; k < ntiles; ++k) {
+            const int d0 = k * TD2, d1 = d0 + TD2;   // only full tile rows can be regular
+            const bool regular = t->irrp && d1 <= t->ncols && d0 >= t->S - 1 && irrp[d1] == irrp[d0 - (t->S - 1)];
+            (regular ? order : irregular).push_back(k);
+        }
+        const int nreg = (int)order.size();
+        order.insert(order.end(), irregular.begin(), irregular.end());
+        int32_t *d = nullptr;
+        LI_CUDA(cudaMalloc(&d, ntiles * sizeof(int32_t)));
+        cudaError_t e = cudaMemcpyAsync(d, order.data(), ntiles * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            set_error("tile list upload failed: %s", cudaGetErrorString(e));
+            return LI_ERR_CUDA;
+        }
+        it = t->tile_rows.emplace(TD2, std::make_pair(d, nreg)).first;
+    }
+    *list = it->second.first;
+    *nregular = it->second.second;
     return LI_OK;
 }
 
@@ -631,6 +703,8 @@ int li_table_destroy(li_table *t)
     cudaFree(t->Wfold);
     cudaFree(t->bfold);
     cudaFree(t->bpf);
+    cudaFree(t->irrp);
+    for (auto &kv : t->tile_rows) cudaFree(kv.second.first);
     delete t;
     return LI_OK;
 }
