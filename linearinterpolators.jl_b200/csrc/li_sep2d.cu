@@ -841,6 +841,40 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     const int ntile_rows = a.tiles2;
     const bool beta = a.beta != (T)0;
     const size_t smem_reg = (2 * ((size_t)ADJ_TD2 * (PT / 2) + 16) + (size_t)NG * 2 * (RG + S2 - 1) * S2) * sizeof(T);
+    static thread_local cudaStream_t side = nullptr;
+    static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    const bool fork = nreg > 0 && ntile_rows - nreg > 0;
+    if (ntile_rows - nreg > 0) {
+        // the few irregular tile rows run concurrently with the regular ones on a side stream (fork / join with
+        // events), otherwise their short launch would serialise behind the main kernel
+        cudaStream_t gst = st;
+        if (fork) {
+            if (!side) {
+                LI_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+                LI_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+                LI_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+            }
+            LI_CUDA(cudaEventRecord(ev_fork, st));   // (before the regular launch: the two kernels overlap)
+            LI_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+            gst = side;
+        }
+        a.rowlist = rowlist + nreg;
+        a.tiles2 = ntile_rows - nreg;
+        const unsigned gblocks = (unsigned)((int64_t)a.tiles1 * a.tiles2 * nbatch);
+        if (beta) {
+            auto kern = sep2d_adj_kernel<T, S1, S2, true>;
+            rc = set_smem(kern, smem);
+            if (rc != LI_OK) return rc;
+            kern<<<gblocks, ADJ_NT, smem, gst>>>(a, TD1, R2);
+        } else {
+            auto kern = sep2d_adj_kernel<T, S1, S2, false>;
+            rc = set_smem(kern, smem);
+            if (rc != LI_OK) return rc;
+            kern<<<gblocks, ADJ_NT, smem, gst>>>(a, TD1, R2);
+        }
+        count_launch();
+        if (fork) LI_CUDA(cudaEventRecord(ev_join, side));
+    }
 #define LI_ADJ_REG(B, RR)                                                                     \
     if (beta == B && R == RR && nreg > 0) {                                                   \
         auto kern = sep2d_adj_regular_kernel<T, S1, S2, B, RR>;                               \
@@ -853,23 +887,7 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     }
     LI_ADJ_REG(false, 1) LI_ADJ_REG(false, 2) LI_ADJ_REG(true, 1) LI_ADJ_REG(true, 2)
 #undef LI_ADJ_REG
-    if (ntile_rows - nreg > 0) {
-        a.rowlist = rowlist + nreg;
-        a.tiles2 = ntile_rows - nreg;
-        const unsigned gblocks = (unsigned)((int64_t)a.tiles1 * a.tiles2 * nbatch);
-        if (beta) {
-            auto kern = sep2d_adj_kernel<T, S1, S2, true>;
-            rc = set_smem(kern, smem);
-            if (rc != LI_OK) return rc;
-            kern<<<gblocks, ADJ_NT, smem, st>>>(a, TD1, R2);
-        } else {
-            auto kern = sep2d_adj_kernel<T, S1, S2, false>;
-            rc = set_smem(kern, smem);
-            if (rc != LI_OK) return rc;
-            kern<<<gblocks, ADJ_NT, smem, st>>>(a, TD1, R2);
-        }
-        count_launch();
-    }
+    if (fork) LI_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     LI_CUDA(cudaGetLastError());
     *done = true;
     return LI_OK;
