@@ -77,6 +77,7 @@ struct li_table {
     // per tile height: device list of tile rows, regular ones first; second = number of regular tile rows
     mutable std::map<int, std::pair<int32_t *, int>> tile_rows;
     mutable std::map<int, int> adjf_rows;
+    mutable std::map<int, int> feed_rows;
     // cached footprint bounds: key = tile rows G -> max over aligned tiles of (max base - min base)
     mutable std::map<int, int> fwd_span;
     // cached: key = tile cols G -> max over aligned column tiles of number of contributing rows
@@ -90,6 +91,9 @@ int table_fwd_span(const li_table *t, int G, cudaStream_t st, int *span);
 int table_adj_rows(const li_table *t, int G, cudaStream_t st, int *rows);
 int table_ensure_fold(const li_table *t, cudaStream_t st);            // needs ncols >= S
 int table_adjf_rows(const li_table *t, int G, cudaStream_t st, int *rows);  // like table_adj_rows, folded bases
+// max over aligned tiles of G columns of the number of rows with a tap landing in the tile (clamped taps included:
+// the first / last column collect every row hanging over that edge)
+int table_feed_rows(const li_table *t, int G, cudaStream_t st, int *rows);
 // tile rows of height TD2 over the columns of t, regular ones (all dst rows fed by exactly reg_R rows, none clamped)
 // first: *list (device) has ntiles entries, the first *nregular of them regular
 int table_tile_rows(const li_table *t, int TD2, cudaStream_t st, const int32_t **list, int *nregular);

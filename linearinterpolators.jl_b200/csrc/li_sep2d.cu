@@ -21,72 +21,9 @@
 #include <algorithm>
 
 #include "li_common.cuh"
+#include "li_sep2d.cuh"
 
 namespace li {
-
-// ---------------------------------------------------------------------------------------------
-template <typename T, int V>
-struct VecT;
-template <>
-struct VecT<float, 4> { using type = float4; };
-template <>
-struct VecT<float, 2> { using type = float2; };
-template <>
-struct VecT<float, 1> { using type = float; };
-template <>
-struct VecT<double, 2> { using type = double2; };
-struct __align__(16) double4a { double x, y, z, w; };   // two 16-byte transactions
-template <>
-struct VecT<double, 4> { using type = double4a; };
-template <>
-struct VecT<double, 1> { using type = double; };
-
-template <typename T, int V>
-struct Pack {
-    T v[V];
-};
-
-template <typename T, int V>
-__device__ __forceinline__ Pack<T, V> ld_pack(const T *p)
-{
-    using VT = typename VecT<T, V>::type;
-    Pack<T, V> r;
-    *reinterpret_cast<VT *>(r.v) = *reinterpret_cast<const VT *>(p);
-    return r;
-}
-
-template <typename T, int V>
-__device__ __forceinline__ void st_pack(T *p, const Pack<T, V> &r)
-{
-    using VT = typename VecT<T, V>::type;
-    *reinterpret_cast<VT *>(p) = *reinterpret_cast<const VT *>(r.v);
-}
-
-template <typename T>
-__device__ __forceinline__ T fmaT(T a, T b, T c);
-template <>
-__device__ __forceinline__ float fmaT<float>(float a, float b, float c) { return fmaf(a, b, c); }
-template <>
-__device__ __forceinline__ double fmaT<double>(double a, double b, double c) { return fma(a, b, c); }
-
-__device__ __forceinline__ int clampi(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
-
-template <typename T>
-struct SepArgs {
-    const int32_t *base1, *base2;  // window bases (canonical, 0-based)
-    const T *W1, *W2;              // [n*S]
-    const int32_t *bp1, *bp2;      // adjoint only: bptr tables (see li_table.cu), [m+S]; bp2 is over FOLDED bases
-    const T *W2f;                  // adjoint only: folded dim-2 weights (li_table.cu: fold_kernel)
-    const int32_t *rowlist;        // adjoint only: tile rows handled by this launch (null: all, in order)
-    int n1, n2;                    // "rows" side (fine grid for an upsampling operator)
-    int m1, m2;                    // "columns" side
-    int tiles1, tiles2;
-    int F1MAX, F2MAX;              // forward: footprint bounds; adjoint: F2MAX = max src rows feeding one row group
-    int vec_ok;                    // rows of the big array are 2-element-vector aligned
-    T alpha, beta;
-    const T *src;
-    T *dst;
-};
 
 // ---------------------------------------------------------------------------------------------
 // Forward: a streaming register pipeline.
@@ -110,57 +47,6 @@ template <int S2>
 struct FwdK {   // source rows per stage: a multiple of S2 (static window rotation)
     static constexpr int value = S2 == 4 ? 8 : (S2 > 4 ? S2 : (S2 == 3 ? 6 : 8));
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// global -> shared bulk copy, completion signalled on an mbarrier (bytes: multiple of 16, both sides 16-byte aligned)
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-template <typename T, int S>
-__device__ __forceinline__ void ld_weights(const T *p, T (&w)[S])
-{
-    // rows of S weights are 16-byte aligned when S*sizeof(T) is a multiple of 16
-    if constexpr ((S * sizeof(T)) % 16 == 0) {
-        constexpr int V = 16 / sizeof(T);
-#pragma unroll
-        for (int k = 0; k < S / V; ++k) {
-            const Pack<T, V> t = ld_pack<T, V>(p + k * V);
-#pragma unroll
-            for (int v = 0; v < V; ++v) w[k * V + v] = t.v[v];
-        }
-    } else {
-#pragma unroll
-        for (int s = 0; s < S; ++s) w[s] = p[s];
-    }
-}
 
 template <typename T, int S1, int S2, bool PAIR, bool BETA>
 __global__ void __launch_bounds__(FWD_NT, (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : 2)
@@ -485,12 +371,23 @@ sep2d_adj_kernel(const SepArgs<T> a, const int TD1, const int R2 /* staged dim-2
                         roff = (roff + SLOT) & RMASK;
                         T w[S2];
                         ld_weights<T, S2>(reinterpret_cast<const T *>(reinterpret_cast<const char *>(pw) + woff), w);
-                        woff += S2 * sizeof(T);
+                        if (vv > 0 && vv < a.m2 - S2) {   // interior windows: every slot is fed
 #pragma unroll
-                        for (int s = 0; s < S2; ++s) {
-                            A0[(u + s) % S2] = fmaT(w[s], y.v[0], A0[(u + s) % S2]);
-                            A1[(u + s) % S2] = fmaT(w[s], y.v[1], A1[(u + s) % S2]);
+                            for (int s = 0; s < S2; ++s) {
+                                A0[(u + s) % S2] = fmaT(w[s], y.v[0], A0[(u + s) % S2]);
+                                A1[(u + s) % S2] = fmaT(w[s], y.v[1], A1[(u + s) % S2]);
+                            }
+                        } else {   // first / last window of the array: only the slots the clamped taps land on
+                            const int b = a.base2[i2lo + (int)(woff / (S2 * sizeof(T)))];
+                            const int lo = clampi(b, a.m2 - 1) - vv, hi = clampi(b + S2 - 1, a.m2 - 1) - vv;
+#pragma unroll
+                            for (int s = 0; s < S2; ++s)
+                                if (s >= lo && s <= hi) {
+                                    A0[(u + s) % S2] = fmaT(w[s], y.v[0], A0[(u + s) % S2]);
+                                    A1[(u + s) % S2] = fmaT(w[s], y.v[1], A1[(u + s) % S2]);
+                                }
                         }
+                        woff += S2 * sizeof(T);
                     }
                     if (vv >= ka) {   // dst row vv is complete
                         tp[0] = A0[u];
@@ -729,17 +626,9 @@ sep2d_adj_regular_kernel(const SepArgs<T> a, const int TD1)
     }
 }
 
+
 // ---------------------------------------------------------------------------------------------
-static const int kSmemLimit = 200 * 1024;
-
-template <typename KernT>
-static int set_smem(KernT kern, size_t smem)
-{
-    if (smem > 48 * 1024) LI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return LI_OK;
-}
-
-static int num_sms()
+int sep2d_num_sms()
 {
     static thread_local int n = 0;
     if (!n) {
@@ -757,7 +646,7 @@ static int launch_fwd(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     constexpr int TO1 = 2 * FWD_NT, K = FwdK<S2>::value;
     a.tiles1 = (a.n1 + TO1 - 1) / TO1;
     // chunks of output rows: about one wave of 4 CTAs per SM, chunk length a multiple of 8 and at most FWD_MAXCR
-    const int64_t target = (int64_t)num_sms() * 4;
+    const int64_t target = (int64_t)sep2d_num_sms() * 4;
     int chunks = (int)std::max<int64_t>(1, (target + a.tiles1 * nbatch - 1) / (a.tiles1 * nbatch));
     int CR = (a.n2 + chunks - 1) / chunks;
     CR = std::min(FWD_MAXCR, std::max(8, (CR + 7) & ~7));
@@ -798,6 +687,12 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
 {
     constexpr int NG = ADJ_NG, PT = 2 * (ADJ_NT / NG), RG = ADJ_TD2 / NG;
     if (a.m2 < S2 || a.m1 < 2) return LI_OK;   // decline: the edge folding needs a full window inside the array
+    // LI_B200_ADJ_DEBUG (timing probes): 1 = no side stream, 2 = skip the generic tile rows, 3 = tile kernels only
+    static const int dbg_mode = getenv("LI_B200_ADJ_DEBUG") ? atoi(getenv("LI_B200_ADJ_DEBUG")) : 0;
+    if (dbg_mode != 3) {   // first choice: the streaming kernel (li_sep2d_adjs.cu); it declines what it cannot stage
+        int rcs = sep2d_adj_stream<T>(a, t1, t2, nbatch, st, done);
+        if (rcs != LI_OK || *done) return rcs;
+    }
     int rc = table_ensure_rowstart(t1, st);
     if (rc == LI_OK) rc = table_ensure_fold(t2, st);
     if (rc != LI_OK) return rc;
@@ -843,14 +738,18 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     const size_t smem_reg = (2 * ((size_t)ADJ_TD2 * (PT / 2) + 16) + (size_t)NG * 2 * (RG + S2 - 1) * S2) * sizeof(T);
     static thread_local cudaStream_t side = nullptr;
     static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    const bool fork = nreg > 0 && ntile_rows - nreg > 0;
-    if (ntile_rows - nreg > 0) {
+    const bool fork = nreg > 0 && ntile_rows - nreg > 0 && dbg_mode == 0;
+    if (ntile_rows - nreg > 0 && dbg_mode != 2) {
         // the few irregular tile rows run concurrently with the regular ones on a side stream (fork / join with
         // events), otherwise their short launch would serialise behind the main kernel
         cudaStream_t gst = st;
         if (fork) {
             if (!side) {
-                LI_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+                // highest priority: its few long-running CTAs must be scheduled as soon as slots free up, not
+                // behind the thousands of queued CTAs of the regular kernel
+                int prio_lo = 0, prio_hi = 0;
+                LI_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+                LI_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
                 LI_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
                 LI_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
             }

@@ -1,0 +1,385 @@
+// li_sep2d_adjs.cuh -- fused 2-D separable interpolation, adjoint, streaming form (K7).
+//
+// Reference: the adjoint of the LazyAlgebra composition A1*A2 of test/benchmarks.jl:27-29, whose factors are the
+// scatter loops of src/tabulated.jl:438-478 / src/sparse.jl:760-800 (same mathematics as src/separable.jl:113-162).
+// Included by li_sep2d_adjs_f32.cu / li_sep2d_adjs_f64.cu, which instantiate it for one element type each.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
+#include "li_sep2d.cuh"
+
+namespace li {
+
+// ---------------------------------------------------------------------------------------------
+// Adjoint, streaming form: the forward kernel's data flow run backwards.
+//
+// A CTA owns a strip of NT dst columns and a chunk of CR dst rows (about one wave of CTAs); a thread owns ONE dst
+// column.  The src rows feeding the chunk stream, in ascending order, through the same ring of TMA bulk copies as
+// in the forward kernel (no per-thread global loads: the LSU pipe only sees shared-memory reads).  For every src
+// row the thread
+//   1. gathers along dim 1 from the staged row: the NU staged values around its column (LDS.64, lanes stride one
+//      vector: conflict free for a 2x operator) times its NU folded taps, kept in registers for the whole kernel;
+//   2. adds the value into S2 accumulators (dst rows v .. v+S2-1) with the row's folded dim-2 weights.
+// dst rows are finished one at a time -- for dst row v every src row whose folded window starts at v, like the
+// tile kernels above -- and stored straight from the accumulator (coalesced along dim 1): no intermediate in
+// shared memory, no barrier besides the ring's, no atomics; the result is deterministic.
+// Values outside a thread's tap list are discarded with selects, not multiplied by zero, so a non-finite src
+// element only reaches the dst elements it feeds in the reference.
+//
+// Chunks whose dst rows are each fed by exactly R src rows with no clamped tap (R = reg_R of the dim-2 table: the
+// interior of a same-rate or 2x resampling; found from the table's irregularity prefix sums) run a statically
+// scheduled loop: one stage of K rows is K/R dst rows, no per-row control flow.  Any other chunk (array edges,
+// irregular rates) runs the generic loop over the per-row counts.  Both loops exist in two copies, chosen per warp:
+// one for warps whose threads all have the usual tap pattern (padding only at the ends of the staged window, cleared
+// with three bit masks) and one with a select per tap.
+constexpr int ADS_NT = 256;
+constexpr int ADS_NSTAGE = 3;
+
+template <int S2>
+struct AdsK {   // src rows per stage: a multiple of 2*S2 so that the static schedule has whole slot rotations
+    static constexpr int value = S2 == 6 ? 12 : 8;
+};
+
+template <typename T, int S1, int S2, int NU, int R>
+__global__ void __launch_bounds__(ADS_NT, (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? 4 : 2)
+sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
+{
+    constexpr int NT = ADS_NT, K = AdsK<S2>::value, NSTAGE = ADS_NSTAGE;
+    constexpr int V = 8 / (int)sizeof(T);   // elements per 8-byte shared-memory load
+    static_assert(NU % V == 0 && NU >= 4 && NU % 2 == 0, "bad NU");
+    static_assert(R == 0 || (K % R == 0 && (K / R) % S2 == 0), "bad stage size");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int P1 = a.F1MAX;                                  // elements per staged row (multiple of 16 bytes)
+    T *sS = reinterpret_cast<T *>(smem_raw);                 // [NSTAGE][K][P1]
+    T *sW2 = sS + (size_t)NSTAGE * K * P1;                   // [NRMAX][S2] alpha * folded dim-2 weights
+    int *sNv = reinterpret_cast<int *>(sW2 + (size_t)NRMAX * S2);   // [CR + 2*S2] src rows whose window starts at a dst row
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sNv + ((CR + 2 * S2 + 1) & ~1));
+
+    const int tid = threadIdx.x;
+    int bid = blockIdx.x;
+    const int strip = bid % a.tiles1;
+    bid /= a.tiles1;
+    const int chunk = bid % a.tiles2;
+    const int64_t batch = bid / a.tiles2;
+    const int c0 = strip * NT, c1 = min(c0 + NT, a.m1);      // owned dst columns
+    const int va = chunk * CR, vb = min(va + CR, a.m2);      // owned dst rows
+    const int v0 = va - (S2 - 1);                            // first dst row the chunk's src rows reach
+    const T *src = a.src + batch * (int64_t)a.n1 * a.n2;
+    T *dst = a.dst + batch * (int64_t)a.m1 * a.m2;
+
+    const int u_lo = c0 == 0 ? 0 : a.bp1[c0];                // first src column with a tap in the strip
+    constexpr int AL = 16 / (int)sizeof(T);
+    const int ulo_a = u_lo & ~(AL - 1);                      // first staged src column (16-byte aligned)
+    const int cv1 = min(P1, a.n1 - ulo_a);                   // staged columns that exist (n1 is a multiple of AL)
+    const int i2lo = a.bp2[va], NR = a.bp2[vb - 1 + S2] - i2lo;   // src rows [i2lo, i2lo + NR)
+    const int NJ = (NR + K - 1) / K;
+    bool regular = false;
+    if constexpr (R > 0) regular = v0 > 0 && vb <= a.m2 - S2 && a.irrp2[vb] == a.irrp2[v0];
+
+    if (tid == 0) {
+#pragma unroll
+        for (int sgi = 0; sgi < NSTAGE; ++sgi) mbar_init(&bar[sgi], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int j) {   // producer (one thread): stage j <- src rows i2lo + j*K ..
+        uint64_t *b = &bar[j % NSTAGE];
+        T *buf = sS + (size_t)(j % NSTAGE) * K * P1;
+        const uint32_t bytes = (uint32_t)(cv1 * sizeof(T));
+        const int nr = min(K, NR - j * K);
+        mbar_expect_tx(b, bytes * nr);
+        for (int r = 0; r < nr; ++r)
+            bulk_g2s(buf + r * P1, src + (int64_t)(i2lo + j * K + r) * a.n1 + ulo_a, bytes, b);
+    };
+    if (tid == 0)
+        for (int j = 0; j < NSTAGE - 1 && j < NJ; ++j) issue(j);
+
+    // chunk metadata: rows per dst row (generic loop only), dim-2 weights
+    const int NV = vb - v0;                                   // dst rows v0 .. vb-1
+    if (!regular)
+        for (int k = tid; k < CR + 2 * S2; k += NT) sNv[k] = k < NV ? a.bp2[va + k + 1] - a.bp2[va + k] : 0;
+    for (int k = tid; k < NR * S2; k += NT) sW2[k] = a.alpha * a.W2f[(int64_t)i2lo * S2 + k];
+
+    // per-thread dim-1 taps: src columns [e0, e1) feed dst column c; staged window starts at a0 <= e0 (vector aligned)
+    const int c = c0 + tid;
+    const bool have = c < c1;
+    const int cc = min(c, a.m1 - 1);
+    const int e0 = cc == 0 ? 0 : a.bp1[cc], e1 = cc == a.m1 - 1 ? a.n1 : a.bp1[cc + S1];
+    const int a0 = e0 & ~(V - 1);
+    T w1[NU];
+    unsigned vm = 0;
+#pragma unroll
+    for (int t = 0; t < NU; ++t) {
+        const int i = a0 + t;
+        w1[t] = (T)0;
+        if (have && i >= e0 && i < e1) {
+            // (a folded window can hold slots that none of the row's clamped taps lands on: those are not fed)
+            const int b = a.base1[i];
+            if (cc >= clampi(b, a.m1 - 1) && cc <= clampi(b + S1 - 1, a.m1 - 1)) {
+                w1[t] = a.W1f[(int64_t)i * S1 + (cc - a.bfold1[i])];
+                vm |= 1u << t;
+            }
+        }
+    }
+    // the usual tap pattern: only the first and the last two staged values can be padding; they are cleared with
+    // bit masks (one LOP3 each).  Warps holding any other pattern (array edges) take the copy with selects.
+    constexpr unsigned MID = ((1u << (NU - 2)) - 1u) & ~1u;
+    const bool warp_clean = __all_sync(0xffffffffu, (vm & MID) == MID);
+    using Bits = typename std::conditional<sizeof(T) == 4, uint32_t, uint64_t>::type;
+    Bits k0 = (vm & 1u) ? ~(Bits)0 : (Bits)0;
+    Bits ka = ((vm >> (NU - 2)) & 1u) ? ~(Bits)0 : (Bits)0;
+    Bits kb = ((vm >> (NU - 1)) & 1u) ? ~(Bits)0 : (Bits)0;
+    int rowstep = P1;
+    // (opaque to the optimiser: otherwise the masks turn back into compare + select pairs and vm into NU flags)
+    if constexpr (sizeof(T) == 4)
+        asm volatile("" : "+r"(k0), "+r"(ka), "+r"(kb), "+r"(vm), "+r"(rowstep));
+    else
+        asm volatile("" : "+l"(k0), "+l"(ka), "+l"(kb), "+r"(vm), "+r"(rowstep));
+    auto keep = [](T x, Bits m) {
+        Bits b;
+        memcpy(&b, &x, sizeof b);
+        b &= m;
+        memcpy(&x, &b, sizeof b);
+        return x;
+    };
+    const int off = a0 - ulo_a;
+    const bool beta = a.beta != (T)0;
+
+    T acc[S2];
+#pragma unroll
+    for (int s = 0; s < S2; ++s) acc[s] = (T)0;
+    T *dp = dst + (int64_t)va * a.m1 + c;
+    __syncthreads();
+
+    // dim 1 of the staged row at p
+    auto gather = [&](const T *p, auto clean) {
+        T x[NU];
+#pragma unroll
+        for (int t = 0; t < NU; t += V) {
+            const Pack<T, V> q = ld_pack<T, V>(p + t);
+#pragma unroll
+            for (int e = 0; e < V; ++e) x[t + e] = q.v[e];
+        }
+        if constexpr (decltype(clean)::value) {
+            x[0] = keep(x[0], k0);
+            x[NU - 2] = keep(x[NU - 2], ka);
+            x[NU - 1] = keep(x[NU - 1], kb);
+        } else {
+            unsigned m = vm;
+            asm volatile("" : "+r"(m));   // (keeps the NU bit tests out of registers)
+#pragma unroll
+            for (int t = 0; t < NU; ++t) x[t] = ((m >> t) & 1u) ? x[t] : (T)0;
+        }
+        T va0 = x[0] * w1[0], va1 = x[1] * w1[1];   // two independent chains
+#pragma unroll
+        for (int t = 2; t < NU; t += 2) {
+            va0 = fmaT(x[t], w1[t], va0);
+            va1 = fmaT(x[t + 1], w1[t + 1], va1);
+        }
+        return va0 + va1;
+    };
+    auto next_stage = [&](int j) {   // block-uniform; returns the first staged row of stage j (this thread's window)
+        __syncthreads();             // every thread is done with stage j-1: its buffer may be refilled
+        if (tid == 0 && j + NSTAGE - 1 < NJ) issue(j + NSTAGE - 1);
+        mbar_wait(&bar[j % NSTAGE], (uint32_t)((j / NSTAGE) & 1));
+        return (const T *)(sS + (size_t)(j % NSTAGE) * K * P1 + off);
+    };
+    auto emit = [&](int vv, T value) {   // dst row vv is complete
+        if (vv >= va) {
+            if (have) {
+                if (beta)
+                    *dp = fmaT(a.beta, *dp, value);
+                else
+                    *dp = value;
+            }
+            dp += a.m1;
+        }
+    };
+
+    // ---- static schedule: stage j holds the R rows of each of the dst rows v0 + j*DR .. + DR-1
+    auto run_regular = [&](auto clean) {
+        if constexpr (R > 0) {
+            constexpr int DR = K / R;
+            const T *pw = sW2;
+            for (int j = 0; j < NJ; ++j) {
+                const T *prow = next_stage(j);
+#pragma unroll
+                for (int d = 0; d < DR; ++d) {
+                    const int vv = v0 + j * DR + d;
+                    if (vv < vb) {   // block-uniform: only the last stage is partial
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const T val = gather(prow, clean);
+                            prow += rowstep;
+                            T w2[S2];
+                            ld_weights<T, S2>(pw + (d * R + r) * S2, w2);
+#pragma unroll
+                            for (int s = 0; s < S2; ++s) acc[(d + s) % S2] = fmaT(w2[s], val, acc[(d + s) % S2]);
+                        }
+                        emit(vv, acc[d % S2]);
+                        acc[d % S2] = (T)0;
+                    }
+                }
+                pw += K * S2;
+            }
+        }
+    };
+
+    // ---- generic schedule: for dst row vv, every src row whose folded window starts at vv
+    auto run_generic = [&](auto clean) {
+        const T *pw = sW2;
+        const int *pn = sNv;
+        const T *prow = sS + off;
+        int left = 0;       // rows of the current stage not yet consumed
+        int j = -1;         // current stage
+        int k = 0;          // rows consumed (only the array-edge path needs it)
+        auto row = [&]() {
+            if (left == 0) {
+                prow = next_stage(++j);
+                left = K;
+            }
+            --left;
+            const T val = gather(prow, clean);
+            prow += rowstep;
+            return val;
+        };
+        for (int v = v0; v < vb; v += S2) {
+#pragma unroll
+            for (int u = 0; u < S2; ++u) {
+                const int vv = v + u;
+                if (vv < vb) {   // block-uniform
+                    int n = pn[u];
+                    if (vv > 0 && vv < a.m2 - S2) {   // interior windows: every slot is fed
+                        k += n;
+#pragma unroll 1
+                        for (; n > 0; --n) {
+                            const T val = row();
+                            T w2[S2];
+                            ld_weights<T, S2>(pw, w2);
+                            pw += S2;
+#pragma unroll
+                            for (int s = 0; s < S2; ++s) acc[(u + s) % S2] = fmaT(w2[s], val, acc[(u + s) % S2]);
+                        }
+                    } else {   // first / last window of the array: only the slots the clamped taps land on
+#pragma unroll 1
+                        for (; n > 0; --n) {
+                            const T val = row();
+                            T w2[S2];
+                            ld_weights<T, S2>(pw, w2);
+                            pw += S2;
+                            const int b = a.base2[i2lo + k];
+                            ++k;
+                            const int lo = clampi(b, a.m2 - 1) - vv, hi = clampi(b + S2 - 1, a.m2 - 1) - vv;
+#pragma unroll
+                            for (int s = 0; s < S2; ++s)
+                                if (s >= lo && s <= hi) acc[(u + s) % S2] = fmaT(w2[s], val, acc[(u + s) % S2]);
+                        }
+                    }
+                    emit(vv, acc[u]);
+                    acc[u] = (T)0;
+                }
+            }
+            pn += S2;
+        }
+    };
+
+    // (every copy runs the same sequence of barriers, so warps of one CTA may take different copies)
+    if (regular) {
+        if (warp_clean)
+            run_regular(std::true_type{});
+        else
+            run_regular(std::false_type{});
+    } else {
+        if (warp_clean)
+            run_generic(std::true_type{});
+        else
+            run_generic(std::false_type{});
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T, int S1, int S2, int NU, int R>
+static int launch_stream(SepArgs<T> &a, int CR, int NRMAX, size_t smem, int64_t blocks, cudaStream_t st)
+{
+    auto kern = sep2d_adj_stream_kernel<T, S1, S2, NU, R>;
+    int rc = set_smem(kern, smem);
+    if (rc != LI_OK) return rc;
+    kern<<<(unsigned)blocks, ADS_NT, smem, st>>>(a, CR, NRMAX);
+    count_launch();
+    LI_CUDA(cudaGetLastError());
+    return LI_OK;
+}
+
+template <typename T, int S1, int S2>
+static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64_t nbatch, cudaStream_t st, bool *done)
+{
+    constexpr int V = 8 / (int)sizeof(T), AL = 16 / (int)sizeof(T), K = AdsK<S2>::value;
+    constexpr int NU_S = (S1 + 2 + 1) & ~1, NU_L = 2 * S1 + 2;   // taps kept per thread: same-rate / 2x operators
+    if (a.m1 < S1 || a.m2 < S2) return LI_OK;                    // folding needs a full window inside the array
+    if (a.n1 % AL != 0 || ((uintptr_t)a.src) % 16 != 0) return LI_OK;   // bulk copies need 16-byte aligned row segments
+    int rc = table_ensure_fold(t1, st);
+    if (rc == LI_OK) rc = table_ensure_fold(t2, st);
+    if (rc != LI_OK) return rc;
+    int maxcount = 0, span = 0;
+    rc = table_feed_rows(t1, 1, st, &maxcount);
+    if (rc == LI_OK) rc = table_feed_rows(t1, ADS_NT, st, &span);
+    if (rc != LI_OK) return rc;
+    const int need = maxcount + (V - 1);
+    static const bool trace = getenv("LI_B200_TRACE") != nullptr;
+    if (need > NU_L) {   // decline (down-sampling along dim 1, or many rows hanging over an edge)
+        if (trace) fprintf(stderr, "[li_b200] adj stream declines: %d taps per dst column > %d\n", need, NU_L);
+        return LI_OK;
+    }
+    const int NU = need <= NU_S ? NU_S : NU_L;
+    const int P1 = (span + (AL - 1) + NU + (AL - 1)) & ~(AL - 1);
+    a.tiles1 = (a.m1 + ADS_NT - 1) / ADS_NT;
+    const int per_sm = (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? 4 : 2;
+    const int64_t target = (int64_t)sep2d_num_sms() * per_sm;
+    const int chunks = (int)std::max<int64_t>(1, (target + a.tiles1 * nbatch - 1) / (a.tiles1 * nbatch));
+    int CR = std::max(8, (a.m2 + chunks - 1) / chunks);
+    CR = std::min(CR, 1024);
+    a.tiles2 = (a.m2 + CR - 1) / CR;
+    int nrmax = 0;
+    rc = table_adjf_rows(t2, CR, st, &nrmax);
+    if (rc != LI_OK) return rc;
+    const int NRMAX = (std::max(nrmax, 1) + 1) & ~1;
+    const size_t smem = ((size_t)ADS_NSTAGE * K * P1 + (size_t)NRMAX * S2) * sizeof(T) +
+                        (size_t)((CR + 2 * S2 + 1) & ~1) * sizeof(int) + ADS_NSTAGE * sizeof(uint64_t);
+    const int R = (t2->irrp && (t2->reg_R == 1 || t2->reg_R == 2)) ? t2->reg_R : 0;
+    if (trace)
+        fprintf(stderr, "[li_b200] adj stream: NU %d P1 %d CR %d NRMAX %d smem %zu tiles %d x %d R %d\n", NU, P1, CR, NRMAX,
+                smem, a.tiles1, a.tiles2, R);
+    if (smem > (size_t)kSmemLimit) return LI_OK;
+    const int64_t blocks = (int64_t)a.tiles1 * a.tiles2 * nbatch;
+    LI_REQUIRE(blocks <= 0x7fffffffLL, LI_ERR_UNSUPPORTED, "too many tiles");
+    a.bp1 = t1->rowstart, a.bfold1 = t1->bfold, a.W1f = (const T *)t1->Wfold;
+    a.bp2 = t2->bpf, a.W2f = (const T *)t2->Wfold, a.irrp2 = t2->irrp;
+    a.F1MAX = P1;
+#define LI_ADS(NUU, RR) \
+    if (NU == NUU && R == RR) rc = launch_stream<T, S1, S2, NUU, RR>(a, CR, NRMAX, smem, blocks, st);
+    LI_ADS(NU_S, 0) LI_ADS(NU_S, 1) LI_ADS(NU_S, 2) LI_ADS(NU_L, 0) LI_ADS(NU_L, 1) LI_ADS(NU_L, 2)
+#undef LI_ADS
+    if (rc == LI_OK) *done = true;
+    return rc;
+}
+
+template <typename T>
+int sep2d_adj_stream(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64_t nbatch, cudaStream_t st, bool *done)
+{
+    const int S1 = t1->S, S2 = t2->S;
+#define LI_SEP(A1, A2) \
+    if (S1 == A1 && S2 == A2) return stream_T<T, A1, A2>(a, t1, t2, nbatch, st, done);
+#ifdef LI_DEV_FAST   // development builds: the headline pair only
+    LI_SEP(4, 4)
+#else
+    LI_SEP(2, 2) LI_SEP(4, 4) LI_SEP(6, 6) LI_SEP(2, 4) LI_SEP(4, 2) LI_SEP(4, 6) LI_SEP(6, 4)
+#endif
+#undef LI_SEP
+    return LI_OK;
+}
+
+}  // namespace li

@@ -195,6 +195,18 @@ __global__ void adj_rows_kernel(const int32_t *__restrict__ bptr, int S, int nco
     atomicMax(out, (int)(bptr[k1 - 1 + S] - bptr[k0]));
 }
 
+// rows [lo, hi) with a tap landing in an aligned tile of G columns, clamped taps included
+__global__ void feed_rows_kernel(const int32_t *__restrict__ rowstart, int S, int ncols, int nrows, int G, int *out)
+{
+    int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    int k0 = tile * G;
+    if (k0 >= ncols) return;
+    int k1 = min(k0 + G, ncols);  // exclusive
+    const int lo = k0 == 0 ? 0 : rowstart[k0];
+    const int hi = k1 == ncols ? nrows : rowstart[k1 - 1 + S];
+    atomicMax(out, hi - lo);
+}
+
 // Fold the clamped taps of a window into the window shifted inside [0, ncols): bc = clamp(base, 0, ncols - S),
 // tap s lands in slot clamp(base + s, 0, ncols-1) - bc.  (Sums of weights that hit the same column.)
 template <typename T>
@@ -513,6 +525,30 @@ int table_adj_rows(const li_table *t, int G, cudaStream_t st, int *rows)
     if (rc != LI_OK) return rc;
     std::lock_guard<std::mutex> lock(t->mu);
     t->adj_rows[G] = v;
+    *rows = v;
+    return LI_OK;
+}
+
+int table_feed_rows(const li_table *t, int G, cudaStream_t st, int *rows)
+{
+    {
+        std::lock_guard<std::mutex> lock(t->mu);
+        auto it = t->feed_rows.find(G);
+        if (it != t->feed_rows.end()) {
+            *rows = it->second;
+            return LI_OK;
+        }
+    }
+    int rc = table_ensure_rowstart(t, st);
+    if (rc != LI_OK) return rc;
+    int v = 0;
+    const int ntiles = (int)((t->ncols + G - 1) / G);
+    rc = reduce_to_host(st, 0, &v, [&](int *d) {
+        feed_rows_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(t->rowstart, t->S, (int)t->ncols, (int)t->nrows, G, d);
+    });
+    if (rc != LI_OK) return rc;
+    std::lock_guard<std::mutex> lock(t->mu);
+    t->feed_rows[G] = v;
     *rows = v;
     return LI_OK;
 }

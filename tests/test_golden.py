@@ -64,8 +64,8 @@ def test_cuda_reproduces_golden_tables_and_applies(gold, ki, cname, cond, T):
     src = np.asfortranarray(gold[f"src_{tag}"])
     y = np.asfortranarray(gold[f"y_{tag}"])
     ok = ~np.isnan(gold[f"dir_{tag}"]).any()
-    d = li.apply(li.Direct, A, src)
-    a = li.apply(li.Adjoint, A, y)
+    d = li.apply(li.Direct, A, 1, src)
+    a = li.apply(li.Adjoint, A, 1, y)
     if ok:
         assert_close(d, gold[f"dir_{tag}"], T, factor=4)
         assert_close(a, gold[f"adj_{tag}"], T, factor=16)

@@ -388,6 +388,12 @@ FUSED_CASES = [
     (KERNELS[8], O.FLAT, KERNELS[8], O.FLAT, (40, 30), (150, 120), "random"),            # non-monotone positions
     (KERNELS[0], O.FLAT, KERNELS[0], O.FLAT, (20, 30), (64, 33), "overhang"),            # S = (1, 1)
     (KERNELS[2], O.SAFEFLAT, KERNELS[2], O.FLAT, (31, 45), (100, 90), "overhang"),       # S = (3, 3)
+    # streaming adjoint (rows of the fine grid 16-byte aligned): several strips and chunks, clamped edges
+    (KERNELS[8], O.FLAT, KERNELS[8], O.FLAT, (600, 300), (1200, 600), "aligned"),
+    (KERNELS[8], O.SAFEFLAT, KERNELS[8], O.SAFEFLAT, (520, 260), (1040, 519), "overhang"),
+    (KERNELS[9], O.FLAT, KERNELS[9], O.FLAT, (300, 100), (600, 200), "aligned"),         # Lanczos-6, 14 taps per thread
+    (KERNELS[1], O.FLAT, KERNELS[1], O.SAFEFLAT, (300, 290), (304, 299), "aligned"),     # S = (2, 2), ~1x
+    (KERNELS[4], O.FLAT, KERNELS[9], O.FLAT, (270, 40), (400, 77), "overhang"),          # S = (4, 6), 1.5x
 ]
 
 
@@ -434,6 +440,27 @@ def test_fused_separable_2d(li, T, case):
     assert_close(H * src, ref, T, factor=8)
     # adjoint identity in Float64 on the host
     np.testing.assert_allclose(li.vdot(out, y), li.vdot(src, back), rtol=3e-5 if T == np.float32 else 1e-11)
+
+
+@pytest.mark.parametrize("n1", [600, 602])   # streaming kernel / tile kernels
+@pytest.mark.parametrize("T", DTYPES)
+def test_fused_adjoint_non_finite_footprint(li, T, n1):
+    """A non-finite sample reaches exactly the dst elements it feeds in the reference (no 0 * Inf leaks)."""
+    rng = np.random.default_rng(5)
+    m1, m2, n2 = 300, 70, 140
+    x1, x2 = np.linspace(1.0, m1, n1), np.linspace(-2.0, m2 + 3.0, n2)
+    ker = li.LanczosKernel(T, 4)
+    A1, A2 = li.TabulatedInterpolator(T, 1, ker, x1, m1), li.TabulatedInterpolator(T, 2, ker, x2, m2)
+    J1, W1 = O.maketable(O.kernel(O.LANCZOS, 4), x1.astype(T), m1, T)
+    J2, W2 = O.maketable(O.kernel(O.LANCZOS, 4), x2.astype(T), m2, T)
+    y = np.asfortranarray(rng.standard_normal((n1, n2)).astype(T))
+    for (i1, i2, bad) in ((0, 0, np.inf), (257, 60, np.nan), (n1 - 1, 139, -np.inf), (300, 3, np.inf)):
+        y[i1, i2] = bad
+    refa = O.tab_adjoint(J2, W2, m2, 2, O.tab_adjoint(J1, W1, m1, 1, y, skip_zero=False), skip_zero=False)
+    back = li.to_host((A1 * A2).adj * li.to_device(y))
+    assert np.array_equal(np.isfinite(back), np.isfinite(refa))
+    ok = np.isfinite(refa)
+    assert_close(np.where(ok, back, 0), np.where(ok, refa, 0), T, factor=64)
 
 
 def test_fused_separable_batch(li):
