@@ -291,8 +291,15 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        dom_ms, dom = (adj_ms, "sep2d_adj_kernel") if adj_ms >= fwd_ms else (fwd_ms, "sep2d_fwd_kernel")
+        dom_ms, dom = (adj_ms, "sep2d_adj_stream_kernel") if adj_ms >= fwd_ms else (fwd_ms, "sep2d_fwd_kernel")
         achieved = ALGO_BYTES_PER_APPLY / (dom_ms * 1e-3) / 1e9
+        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if any
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(dom)
+        except (OSError, ValueError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -301,7 +308,7 @@ def run_b200(args):
                        "l2": "inputs rotate over 2 buffer sets of 671 MB each (> 126 MB L2); no timed kernel re-reads fresh data",
                        "host_wall_ms_per_step": 1e3 * t_host / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_APPLY,
                          "fwd_ms": fwd_ms, "adj_ms": adj_ms,
                          "fwd_frac": ALGO_BYTES_PER_APPLY / (fwd_ms * 1e-3) / 1e9 / peak,

@@ -31,6 +31,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra flags for experiments, e.g. LI_NVCC_EXTRA="-DLI_DEV_FAST -DADS_NT_=128"
+NVCC_FLAGS += os.environ.get("LI_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):

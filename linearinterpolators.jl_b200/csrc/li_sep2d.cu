@@ -40,7 +40,13 @@ namespace li {
 // The dim-1 result never touches shared memory, no source row is re-computed, and src/dst cross HBM once.
 // Flat/SafeFlat clamping is applied while staging (clamped row index for the copy, replicated edge columns).
 constexpr int FWD_NT = 256;
-constexpr int FWD_NSTAGE = 3;
+#ifndef FWD_NSTAGE_
+#define FWD_NSTAGE_ 3
+#endif
+#ifndef FWD_WAVES_
+#define FWD_WAVES_ 2
+#endif
+constexpr int FWD_NSTAGE = FWD_NSTAGE_;
 constexpr int FWD_MAXCR = 256;   // output rows per chunk (one thread per row when counting completions)
 
 template <int S2>
@@ -646,7 +652,7 @@ static int launch_fwd(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     constexpr int TO1 = 2 * FWD_NT, K = FwdK<S2>::value;
     a.tiles1 = (a.n1 + TO1 - 1) / TO1;
     // chunks of output rows: about one wave of 4 CTAs per SM, chunk length a multiple of 8 and at most FWD_MAXCR
-    const int64_t target = (int64_t)sep2d_num_sms() * 4;
+    const int64_t target = (int64_t)sep2d_num_sms() * 4 * FWD_WAVES_;
     int chunks = (int)std::max<int64_t>(1, (target + a.tiles1 * nbatch - 1) / (a.tiles1 * nbatch));
     int CR = (a.n2 + chunks - 1) / chunks;
     CR = std::min(FWD_MAXCR, std::max(8, (CR + 7) & ~7));

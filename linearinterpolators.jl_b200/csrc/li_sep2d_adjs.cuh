@@ -35,16 +35,29 @@ namespace li {
 // irregular rates) runs the generic loop over the per-row counts.  Both loops exist in two copies, chosen per warp:
 // one for warps whose threads all have the usual tap pattern (padding only at the ends of the staged window, cleared
 // with three bit masks) and one with a select per tap.
-constexpr int ADS_NT = 256;
-constexpr int ADS_NSTAGE = 3;
+#ifndef ADS_NT_
+#define ADS_NT_ 256
+#endif
+#ifndef ADS_NSTAGE_
+#define ADS_NSTAGE_ 2
+#endif
+#ifndef ADS_K_
+#define ADS_K_ 8
+#endif
+#ifndef ADS_WAVES_
+#define ADS_WAVES_ 1
+#endif
+constexpr int ADS_NT = ADS_NT_;
+constexpr int ADS_NSTAGE = ADS_NSTAGE_;
+constexpr int ADS_PER_SM = 4 * 256 / ADS_NT;   // CTAs per SM of the 4-byte, <= 10-tap kernels
 
 template <int S2>
 struct AdsK {   // src rows per stage: a multiple of 2*S2 so that the static schedule has whole slot rotations
-    static constexpr int value = S2 == 6 ? 12 : 8;
+    static constexpr int value = S2 == 6 ? 12 : ADS_K_;
 };
 
 template <typename T, int S1, int S2, int NU, int R>
-__global__ void __launch_bounds__(ADS_NT, (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? 4 : 2)
+__global__ void __launch_bounds__(ADS_NT, (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? ADS_PER_SM : ADS_PER_SM / 2)
 sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 {
     constexpr int NT = ADS_NT, K = AdsK<S2>::value, NSTAGE = ADS_NSTAGE;
@@ -134,11 +147,12 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
     Bits ka = ((vm >> (NU - 2)) & 1u) ? ~(Bits)0 : (Bits)0;
     Bits kb = ((vm >> (NU - 1)) & 1u) ? ~(Bits)0 : (Bits)0;
     int rowstep = P1;
+    int dstep = a.m1;
     // (opaque to the optimiser: otherwise the masks turn back into compare + select pairs and vm into NU flags)
     if constexpr (sizeof(T) == 4)
-        asm volatile("" : "+r"(k0), "+r"(ka), "+r"(kb), "+r"(vm), "+r"(rowstep));
+        asm volatile("" : "+r"(k0), "+r"(ka), "+r"(kb), "+r"(vm), "+r"(rowstep), "+r"(dstep));
     else
-        asm volatile("" : "+l"(k0), "+l"(ka), "+l"(kb), "+r"(vm), "+r"(rowstep));
+        asm volatile("" : "+l"(k0), "+l"(ka), "+l"(kb), "+r"(vm), "+r"(rowstep), "+r"(dstep));
     auto keep = [](T x, Bits m) {
         Bits b;
         memcpy(&b, &x, sizeof b);
@@ -157,6 +171,9 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 
     // dim 1 of the staged row at p
     auto gather = [&](const T *p, auto clean) {
+#ifdef ADS_ABLATE
+        if (a.vec_ok == 77) return p[0];   // timing probe: the ring without the dim-1 gather
+#endif
         T x[NU];
 #pragma unroll
         for (int t = 0; t < NU; t += V) {
@@ -188,15 +205,15 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
         mbar_wait(&bar[j % NSTAGE], (uint32_t)((j / NSTAGE) & 1));
         return (const T *)(sS + (size_t)(j % NSTAGE) * K * P1 + off);
     };
+    const bool ld_old = beta && have;
+    const T betav = a.beta;
     auto emit = [&](int vv, T value) {   // dst row vv is complete
         if (vv >= va) {
-            if (have) {
-                if (beta)
-                    *dp = fmaT(a.beta, *dp, value);
-                else
-                    *dp = value;
-            }
-            dp += a.m1;
+            T old = (T)0;
+            if (ld_old) old = *dp;                     // (beta == 0: dst is never read)
+            const T o = beta ? fmaT(betav, old, value) : value;
+            if (have) *dp = o;
+            dp += dstep;
         }
     };
 
@@ -337,8 +354,8 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     const int NU = need <= NU_S ? NU_S : NU_L;
     const int P1 = (span + (AL - 1) + NU + (AL - 1)) & ~(AL - 1);
     a.tiles1 = (a.m1 + ADS_NT - 1) / ADS_NT;
-    const int per_sm = (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? 4 : 2;
-    const int64_t target = (int64_t)sep2d_num_sms() * per_sm;
+    const int per_sm = (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? ADS_PER_SM : ADS_PER_SM / 2;
+    const int64_t target = (int64_t)sep2d_num_sms() * per_sm * ADS_WAVES_;
     const int chunks = (int)std::max<int64_t>(1, (target + a.tiles1 * nbatch - 1) / (a.tiles1 * nbatch));
     int CR = std::max(8, (a.m2 + chunks - 1) / chunks);
     CR = std::min(CR, 1024);
@@ -359,6 +376,9 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     a.bp1 = t1->rowstart, a.bfold1 = t1->bfold, a.W1f = (const T *)t1->Wfold;
     a.bp2 = t2->bpf, a.W2f = (const T *)t2->Wfold, a.irrp2 = t2->irrp;
     a.F1MAX = P1;
+#ifdef ADS_ABLATE
+    if (getenv("LI_B200_ADJ_DEBUG") && atoi(getenv("LI_B200_ADJ_DEBUG")) == 4) a.vec_ok = 77;
+#endif
 #define LI_ADS(NUU, RR) \
     if (NU == NUU && R == RR) rc = launch_stream<T, S1, S2, NUU, RR>(a, CR, NRMAX, smem, blocks, st);
     LI_ADS(NU_S, 0) LI_ADS(NU_S, 1) LI_ADS(NU_S, 2) LI_ADS(NU_L, 0) LI_ADS(NU_L, 1) LI_ADS(NU_L, 2)
