@@ -91,8 +91,11 @@ template <typename T, int S1, int S2>
 __global__ void __launch_bounds__(256)
 affine_adjoint_atomic_kernel(AffineArgs<T> a, const T *__restrict__ src, T *__restrict__ dst, int *__restrict__ err)
 {
-    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i2 = blockIdx.y * blockDim.y + threadIdx.y;
+    // a warp covers an 8 x 4 patch of pixels (block = 64 x 4 pixels = 8 patches side by side): whatever the rotation,
+    // the 32 atomics of one instruction land in a compact 2-D neighbourhood, i.e. on few cache lines
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int i1 = blockIdx.x * 64 + w * 8 + (lane & 7);
+    const int i2 = blockIdx.y * 4 + (lane >> 3);
     if (i1 >= a.n1 || i2 >= a.n2) return;
     T w1[S1], w2[S2];
     int b1, b2;
