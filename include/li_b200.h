@@ -175,7 +175,9 @@ LI_API int li_sep_apply(int adjoint, int ndim, const li_table *const *tabs, cons
 /* n independent separable applies in one call (one launch sequence, no per-call host overhead): apply k uses
  * tabs[k*ndim .. k*ndim+ndim-1], src_dev[k] and dst_dev[k].  Several applies may share one dst (beta = 1): they are
  * executed in order on `stream`, which is how `m = sum_k A_k' y_k` of iterative fitting (README: "A'*y") is
- * accumulated.  Intermediate workspace, if any apply needs it, is managed by the library. */
+ * accumulated.  Intermediate workspace, if any apply needs it, is managed by the library.  A long batch of fused 2-D
+ * applies into ONE dst with beta = 1 is dealt round-robin to a few internal streams with partial accumulators that
+ * are summed in a fixed order at the end (deterministic; the sum is associated differently from the in-order one). */
 LI_API int li_sep_apply_batch(int adjoint, int ndim, int64_t n, const li_table *const *tabs, const int64_t *dims_other,
                               int64_t nbatch, double alpha, const void *const *src_dev, double beta,
                               void *const *dst_dev, int variant, void *stream);

@@ -45,8 +45,8 @@ int vscale_impl(int dtype, void *y, int64_t n, double beta, cudaStream_t st)
 // cudaMalloc/cudaFree per call would dominate small applies and serialise the device, and calls on different
 // streams must not share buffers.
 struct StageSet {
-    void *ptr[3] = {nullptr, nullptr, nullptr};
-    size_t bytes[3] = {0, 0, 0};
+    void *ptr[4] = {nullptr, nullptr, nullptr, nullptr};   // 0: src, 1: dst, 2: workspace, 3: partial accumulators
+    size_t bytes[4] = {0, 0, 0, 0};
 };
 static thread_local std::map<void *, StageSet> g_stage;
 

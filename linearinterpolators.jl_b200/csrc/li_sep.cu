@@ -4,6 +4,7 @@
 // Reference: LazyAlgebra composition of per-dimension operators
 // (test/benchmarks.jl:27-29,44-49; H*x = A_1*(...*(A_n*x)), H'*y = A_n'*(...*(A_1'*y)))
 // and the on-the-fly operators src/unidimensional.jl:95-245, src/separable.jl:56-162.
+#include <algorithm>
 #include <vector>
 
 #include "li_common.cuh"
@@ -134,6 +135,92 @@ static int sep_apply_impl(int adjoint, int ndim, const li_table *const *tabs, co
 
 }  // namespace li
 
+namespace li {
+
+template <typename T>
+__global__ void sum_partials_kernel(T *__restrict__ dst, const T *__restrict__ part, int64_t n, int np)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T v = dst[i];
+        for (int k = 0; k < np; ++k) v += part[(int64_t)k * n + i];   // fixed order: deterministic
+        dst[i] = v;
+    }
+}
+
+// Many fused 2-D applies accumulated into ONE destination (dst_k all equal, e.g. m = beta*m + alpha * sum_k H_k' y_k,
+// the inner loop of an iterative fit): one apply is a short, latency-bound kernel and a chain of them on one stream
+// leaves the machine mostly idle, so the frames are dealt round-robin to NSTR streams, each accumulating into its own
+// partial result (stream 0 straight into dst), and the partials are added in a fixed order at the end.  The
+// assignment of frames to streams is static, so the result is deterministic.  *ndone = number of leading frames
+// that were accumulated (0 when the batch is not of that form; less than n when a fused kernel declined a frame --
+// the caller continues from there one frame at a time).
+int sep_accumulate_concurrent(int adjoint, int ndim, int64_t n, const li_table *const *tabs, const int64_t *dims_other,
+                              int64_t nbatch, double alpha, const void *const *src_dev, double beta, void *const *dst_dev,
+                              int variant, void *stream, int64_t *ndone)
+{
+    constexpr int NSTR = 4;
+    *ndone = 0;
+    // (beta must be 1: with any other value the in-order semantics rescales the sum at every frame)
+    if (ndim != 2 || n < 2 * NSTR || variant == LI_VARIANT_ATOMIC || alpha == 0.0 || beta != 1.0) return LI_OK;
+    for (int64_t k = 0; k < n; ++k) {
+        const li_table *const *tk = tabs + k * ndim;
+        if (dst_dev[k] != dst_dev[0] || !tk[0] || !tk[1] || !sep2d_fused_supported(tk[0], tk[1])) return LI_OK;
+        if (tk[0]->dtype != tabs[0]->dtype) return LI_OK;
+        // same destination shape for every frame
+        const int64_t a0 = adjoint ? tk[0]->ncols : tk[0]->nrows, a1 = adjoint ? tk[1]->ncols : tk[1]->nrows;
+        const int64_t b0 = adjoint ? tabs[0]->ncols : tabs[0]->nrows, b1 = adjoint ? tabs[1]->ncols : tabs[1]->nrows;
+        if (a0 != b0 || a1 != b1) return LI_OK;
+    }
+    cudaStream_t st = as_stream(stream);
+    const int dtype = tabs[0]->dtype;
+    const int64_t nout = (adjoint ? tabs[0]->ncols * tabs[1]->ncols : tabs[0]->nrows * tabs[1]->nrows) * nbatch;
+    if (nout <= 0) return LI_OK;
+    void *part = nullptr;
+    int rc = staging(3, (size_t)(NSTR - 1) * nout * dtype_size(dtype), &part, stream);
+    if (rc != LI_OK) return rc;
+    static thread_local cudaStream_t side[NSTR - 1] = {};
+    static thread_local cudaEvent_t ev_fork = nullptr, ev_join[NSTR - 1] = {};
+    if (!ev_fork) {
+        LI_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        for (int s = 0; s < NSTR - 1; ++s) {
+            LI_CUDA(cudaStreamCreateWithFlags(&side[s], cudaStreamNonBlocking));
+            LI_CUDA(cudaEventCreateWithFlags(&ev_join[s], cudaEventDisableTiming));
+        }
+    }
+    // one-off table metadata is built on the caller's stream before the fork (those builds synchronise)
+    LI_CUDA(cudaEventRecord(ev_fork, st));
+    for (int s = 0; s < NSTR - 1; ++s) LI_CUDA(cudaStreamWaitEvent(side[s], ev_fork, 0));
+    int64_t k = 0;
+    for (; k < n; ++k) {
+        const int s = (int)(k % NSTR);
+        cudaStream_t sk = s == 0 ? st : side[s - 1];
+        void *target = s == 0 ? dst_dev[0] : (void *)((char *)part + (size_t)(s - 1) * nout * dtype_size(dtype));
+        const double bk = k >= NSTR ? 1.0 : (s == 0 ? beta : 0.0);   // first use of a target: dst keeps beta, partials start at 0
+        bool ok = false;
+        rc = sep2d_fused_apply(adjoint, tabs[k * ndim], tabs[k * ndim + 1], nbatch, alpha, src_dev[k], bk, target, sk, &ok);
+        if (rc != LI_OK || !ok) break;   // (declined: the caller finishes the batch frame by frame)
+    }
+    for (int s = 0; s < NSTR - 1; ++s) {   // always join, also on errors
+        cudaEventRecord(ev_join[s], side[s]);
+        cudaStreamWaitEvent(st, ev_join[s], 0);
+    }
+    if (rc != LI_OK) return rc;
+    const int np = (int)std::min<int64_t>(k, NSTR) - 1;   // partial accumulators in use
+    if (np > 0) {
+        const unsigned blocks = (unsigned)std::min<int64_t>((nout + 255) / 256, 148 * 8);
+        if (dtype == LI_F32)
+            sum_partials_kernel<float><<<blocks, 256, 0, st>>>((float *)dst_dev[0], (const float *)part, nout, np);
+        else
+            sum_partials_kernel<double><<<blocks, 256, 0, st>>>((double *)dst_dev[0], (const double *)part, nout, np);
+        LI_CHECK_LAUNCH();
+    }
+    *ndone = k;
+    return LI_OK;
+}
+
+}  // namespace li
+
 extern "C" {
 
 int li_sep_workspace_bytes(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other,
@@ -164,7 +251,14 @@ int li_sep_apply_batch(int adjoint, int ndim, int64_t n, const li_table *const *
 {
     LI_REQUIRE(n >= 0 && tabs && (n == 0 || (src_dev && dst_dev)), LI_ERR_ARG, "null argument");
     cudaStream_t st = li::as_stream(stream);
-    for (int64_t k = 0; k < n; ++k) {
+    int64_t k0 = 0;
+    {
+        int rc = li::sep_accumulate_concurrent(adjoint, ndim, n, tabs, dims_other, nbatch, alpha, src_dev, beta, dst_dev,
+                                               variant, stream, &k0);
+        if (rc != LI_OK) return rc;
+        if (k0 > 0) beta = 1.0;   // the destination already holds beta*dst + the first k0 frames
+    }
+    for (int64_t k = k0; k < n; ++k) {
         const li_table *const *tk = tabs + k * ndim;
         size_t need = 0;
         int rc = li_sep_workspace_bytes(adjoint, ndim, tk, dims_other, nbatch, &need);
