@@ -205,14 +205,21 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
         mbar_wait(&bar[j % NSTAGE], (uint32_t)((j / NSTAGE) & 1));
         return (const T *)(sS + (size_t)(j % NSTAGE) * K * P1 + off);
     };
+    // beta != 0: the old values of the thread's dst column are read S2 rows ahead of their use (slot = row mod S2,
+    // like the accumulators), so that the read-modify-write of a dst row never waits for memory
     const bool ld_old = beta && have;
     const T betav = a.beta;
-    auto emit = [&](int vv, T value) {   // dst row vv is complete
+    T oldv[S2];
+#pragma unroll
+    for (int i = 0; i < S2; ++i) {
+        oldv[(S2 - 1 + i) % S2] = (T)0;
+        if (ld_old && va + i < vb) oldv[(S2 - 1 + i) % S2] = dp[(int64_t)i * dstep];   // (beta == 0: dst is never read)
+    }
+    auto emit = [&](int vv, T value, int slot) {   // dst row vv is complete; slot = (vv - v0) % S2, static at every call
         if (vv >= va) {
-            T old = (T)0;
-            if (ld_old) old = *dp;                     // (beta == 0: dst is never read)
-            const T o = beta ? fmaT(betav, old, value) : value;
+            const T o = beta ? fmaT(betav, oldv[slot], value) : value;
             if (have) *dp = o;
+            if (ld_old && vv + S2 < vb) oldv[slot] = dp[(int64_t)S2 * dstep];
             dp += dstep;
         }
     };
@@ -237,7 +244,7 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 #pragma unroll
                             for (int s = 0; s < S2; ++s) acc[(d + s) % S2] = fmaT(w2[s], val, acc[(d + s) % S2]);
                         }
-                        emit(vv, acc[d % S2]);
+                        emit(vv, acc[d % S2], d % S2);
                         acc[d % S2] = (T)0;
                     }
                 }
@@ -296,7 +303,7 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
                                 if (s >= lo && s <= hi) acc[(u + s) % S2] = fmaT(w2[s], val, acc[(u + s) % S2]);
                         }
                     }
-                    emit(vv, acc[u]);
+                    emit(vv, acc[u], u);
                     acc[u] = (T)0;
                 }
             }
@@ -354,10 +361,11 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     const int NU = need <= NU_S ? NU_S : NU_L;
     const int P1 = (span + (AL - 1) + NU + (AL - 1)) & ~(AL - 1);
     a.tiles1 = (a.m1 + ADS_NT - 1) / ADS_NT;
-    const int per_sm = (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? ADS_PER_SM : ADS_PER_SM / 2;
-    const int64_t target = (int64_t)sep2d_num_sms() * per_sm * ADS_WAVES_;
+    // chunks of dst rows: about ADS_PER_SM CTAs per SM (a thread walks its rows one after the other, so a small problem
+    // cut into few long chunks is latency-bound), but at least 4*S2 rows per chunk (each chunk re-reads S2-1 halo rows)
+    const int64_t target = (int64_t)sep2d_num_sms() * ADS_PER_SM * ADS_WAVES_;
     const int chunks = (int)std::max<int64_t>(1, (target + a.tiles1 * nbatch - 1) / (a.tiles1 * nbatch));
-    int CR = std::max(8, (a.m2 + chunks - 1) / chunks);
+    int CR = std::max(std::max(8, 4 * S2), (a.m2 + chunks - 1) / chunks);
     CR = std::min(CR, 1024);
     a.tiles2 = (a.m2 + CR - 1) / CR;
     int nrmax = 0;
