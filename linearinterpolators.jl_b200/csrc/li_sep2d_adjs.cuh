@@ -49,7 +49,10 @@ namespace li {
 #endif
 constexpr int ADS_NT = ADS_NT_;
 constexpr int ADS_NSTAGE = ADS_NSTAGE_;
-constexpr int ADS_PER_SM = 4 * 256 / ADS_NT;   // CTAs per SM of the 4-byte, <= 10-tap kernels
+#ifndef ADS_OCC_
+#define ADS_OCC_ 4
+#endif
+constexpr int ADS_PER_SM = ADS_OCC_ * 256 / ADS_NT;   // CTAs per SM of the 4-byte, <= 10-tap kernels
 
 template <int S2>
 struct AdsK {   // src rows per stage: a multiple of 2*S2 so that the static schedule has whole slot rotations

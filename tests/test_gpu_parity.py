@@ -423,6 +423,9 @@ FUSED_CASES = [
     (KERNELS[9], O.FLAT, KERNELS[9], O.FLAT, (300, 100), (600, 200), "aligned"),         # Lanczos-6, 14 taps per thread
     (KERNELS[1], O.FLAT, KERNELS[1], O.SAFEFLAT, (300, 290), (304, 299), "aligned"),     # S = (2, 2), ~1x
     (KERNELS[4], O.FLAT, KERNELS[9], O.FLAT, (270, 40), (400, 77), "overhang"),          # S = (4, 6), 1.5x
+    (KERNELS[4], O.FLAT, KERNELS[4], O.FLAT, (300, 200), (44, 28), "aligned"),           # down-sampling: dst rows without any src row
+    (KERNELS[8], O.FLAT, KERNELS[8], O.FLAT, (100, 60), (300, 180), "aligned"),          # 3x: too many taps per column -> tile kernels
+    (KERNELS[8], O.SAFEFLAT, KERNELS[8], O.FLAT, (260, 300), (520, 304), "overhang"),    # 2x along dim 1, ~1x along dim 2
 ]
 
 
