@@ -103,22 +103,65 @@ affine_adjoint_atomic_kernel(AffineArgs<T> a, const T *__restrict__ src, T *__re
         atomicExch(err, 1);
         return;
     }
-    int j1[S1];
-    int64_t o2[S2];
-#pragma unroll
-    for (int s = 0; s < S1; ++s) j1[s] = clampi(b1 + s, a.m1 - 1);
-#pragma unroll
-    for (int s = 0; s < S2; ++s) o2[s] = (int64_t)clampi(b2 + s, a.m2 - 1) * a.m1;
     const int64_t splane = (int64_t)a.n1 * a.n2, dplane = (int64_t)a.m1 * a.m2;
+    const bool inner = b1 >= 0 && b1 + S1 <= a.m1 && b2 >= 0 && b2 + S2 <= a.m2;
+    if (inner) {   // no clamped tap: S1*S2 distinct targets
+        const int64_t o0 = (int64_t)b2 * a.m1 + b1;
+        for (int64_t b = blockIdx.z; b < a.nbatch; b += gridDim.z) {
+            T val = src[b * splane + (int64_t)i2 * a.n1 + i1];
+            if (a.alpha != (T)1) val = a.alpha * val;
+            T *dp = dst + b * dplane + o0;
+#pragma unroll
+            for (int s2 = 0; s2 < S2; ++s2) {
+                const T tmp = w2[s2] * val;   // :225-232
+#pragma unroll
+                for (int s1 = 0; s1 < S1; ++s1) atomicAdd(dp + (int64_t)s2 * a.m1 + s1, w1[s1] * tmp);
+            }
+        }
+        return;
+    }
+    // Pixels with clamped taps (at or beyond the border of the destination): many of them land on the same few
+    // border elements -- whole regions of a rotated frame do -- and plain atomics would serialise there.  The taps
+    // that clamp onto one element are summed first (per dimension), then lanes of the warp that target the same
+    // element are combined with shuffles and only one of them issues the atomic.
+    const int t1 = clampi(b1, a.m1 - 1), n1d = clampi(b1 + S1 - 1, a.m1 - 1) - t1 + 1;
+    const int t2 = clampi(b2, a.m2 - 1), n2d = clampi(b2 + S2 - 1, a.m2 - 1) - t2 + 1;
+    T f1[S1], f2[S2];
+#pragma unroll
+    for (int k = 0; k < S1; ++k) {
+        f1[k] = (T)0;
+#pragma unroll
+        for (int s = 0; s < S1; ++s)
+            if (clampi(b1 + s, a.m1 - 1) - t1 == k) f1[k] += w1[s];
+    }
+#pragma unroll
+    for (int k = 0; k < S2; ++k) {
+        f2[k] = (T)0;
+#pragma unroll
+        for (int s = 0; s < S2; ++s)
+            if (clampi(b2 + s, a.m2 - 1) - t2 == k) f2[k] += w2[s];
+    }
     for (int64_t b = blockIdx.z; b < a.nbatch; b += gridDim.z) {
         T val = src[b * splane + (int64_t)i2 * a.n1 + i1];
         if (a.alpha != (T)1) val = a.alpha * val;
         T *dp = dst + b * dplane;
 #pragma unroll
-        for (int s2 = 0; s2 < S2; ++s2) {
-            const T tmp = w2[s2] * val;
+        for (int k2 = 0; k2 < S2; ++k2) {
 #pragma unroll
-            for (int s1 = 0; s1 < S1; ++s1) atomicAdd(dp + o2[s2] + j1[s1], w1[s1] * tmp);
+            for (int k1 = 0; k1 < S1; ++k1) {
+                if (k2 < n2d && k1 < n1d) {
+                    const long long tgt = (long long)(t2 + k2) * a.m1 + (t1 + k1);
+                    T v = f1[k1] * (f2[k2] * val);
+                    const unsigned act = __activemask();
+                    const unsigned peers = __match_any_sync(act, tgt);
+                    const int leader = __ffs(peers) - 1;
+                    for (unsigned m = peers & (peers - 1); m; m &= m - 1) {   // the other lanes of the group, in lane order
+                        const T o = __shfl_sync(peers, v, __ffs(m) - 1);
+                        if ((int)(threadIdx.x + threadIdx.y * blockDim.x) % 32 == leader) v += o;
+                    }
+                    if ((int)(threadIdx.x + threadIdx.y * blockDim.x) % 32 == leader) atomicAdd(dp + tgt, v);
+                }
+            }
         }
     }
 }
