@@ -78,6 +78,13 @@ struct li_table {
     mutable std::map<int, std::pair<int32_t *, int>> tile_rows;
     mutable std::map<int, int> adjf_rows;
     mutable std::map<int, int> feed_rows;
+    // streaming adjoint: cost-balanced chunks of columns, key = number of chunks:
+    // (device array of nchunks+1 boundaries, longest chunk, most rows feeding one chunk)
+    struct ChunkPlan {
+        int32_t *starts = nullptr;
+        int crmax = 0, nrmax = 0;
+    };
+    mutable std::map<int, ChunkPlan> chunk_plans;
     // cached footprint bounds: key = tile rows G -> max over aligned tiles of (max base - min base)
     mutable std::map<int, int> fwd_span;
     // cached: key = tile cols G -> max over aligned column tiles of number of contributing rows
@@ -97,6 +104,11 @@ int table_feed_rows(const li_table *t, int G, cudaStream_t st, int *rows);
 // tile rows of height TD2 over the columns of t, regular ones (all dst rows fed by exactly reg_R rows, none clamped)
 // first: *list (device) has ntiles entries, the first *nregular of them regular
 int table_tile_rows(const li_table *t, int TD2, cudaStream_t st, const int32_t **list, int *nregular);
+// `nchunks` chunks of columns of about equal cost for the streaming adjoint: a chunk holding a column that is not
+// fed by exactly reg_R rows (or touches a folded window) runs the slower generic loop and is made shorter by `penalty`
+// (fraction of a chunk).  *starts (device) has nchunks+1 boundaries.
+int table_chunk_plan(const li_table *t, int nchunks, double penalty, cudaStream_t st, const int32_t **starts, int *crmax,
+                     int *nrmax);
 // builds a table from device positions into preallocated device arrays (used by the OTF operators)
 int table_create_impl(const li_kernel_desc *ker, const void *pos_dev, int64_t nrows, int64_t ncols,
                       cudaStream_t st, li_table **out);

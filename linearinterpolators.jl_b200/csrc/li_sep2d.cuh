@@ -63,6 +63,7 @@ struct SepArgs {
     const int32_t *rowlist;        // adjoint only: tile rows handled by this launch (null: all, in order)
     const int32_t *bfold1;         // streaming adjoint: folded dim-1 bases
     const int32_t *irrp2;          // streaming adjoint: irregularity prefix sums of the dim-2 table (li_table.cu)
+    const int32_t *cstart;         // streaming adjoint: first dst row of every chunk, [tiles2 + 1] (cost-balanced)
     const T *W1f;                  // streaming adjoint: folded dim-1 weights
     int n1, n2;                    // "rows" side (fine grid for an upsampling operator)
     int m1, m2;                    // "columns" side

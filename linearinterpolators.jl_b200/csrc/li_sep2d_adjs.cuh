@@ -82,7 +82,8 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
     const int chunk = bid % a.tiles2;
     const int64_t batch = bid / a.tiles2;
     const int c0 = strip * NT, c1 = min(c0 + NT, a.m1);      // owned dst columns
-    const int va = chunk * CR, vb = min(va + CR, a.m2);      // owned dst rows
+    const int va = a.cstart[chunk], vb = a.cstart[chunk + 1];   // owned dst rows (chunks of about equal cost, <= CR rows)
+    if (va >= vb) return;                                    // (empty chunk: block-uniform, before any barrier)
     const int v0 = va - (S2 - 1);                            // first dst row the chunk's src rows reach
     const T *src = a.src + batch * (int64_t)a.n1 * a.n2;
     T *dst = a.dst + batch * (int64_t)a.m1 * a.m2;
@@ -194,13 +195,23 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 #pragma unroll
             for (int t = 0; t < NU; ++t) x[t] = ((m >> t) & 1u) ? x[t] : (T)0;
         }
-        T va0 = x[0] * w1[0], va1 = x[1] * w1[1];   // two independent chains
+        if constexpr (sizeof(T) == 4) {
+            // two chains (even / odd staged values) as packed FP32x2 operations (FMUL2 / FFMA2, sm_100): the pairs
+            // are exactly what the 8-byte shared-memory loads deliver
+            float2 acc2 = __fmul2_rn(make_float2(x[0], x[1]), make_float2(w1[0], w1[1]));
 #pragma unroll
-        for (int t = 2; t < NU; t += 2) {
-            va0 = fmaT(x[t], w1[t], va0);
-            va1 = fmaT(x[t + 1], w1[t + 1], va1);
+            for (int t = 2; t < NU; t += 2)
+                acc2 = __ffma2_rn(make_float2(x[t], x[t + 1]), make_float2(w1[t], w1[t + 1]), acc2);
+            return (T)(acc2.x + acc2.y);
+        } else {
+            T va0 = x[0] * w1[0], va1 = x[1] * w1[1];   // two independent chains
+#pragma unroll
+            for (int t = 2; t < NU; t += 2) {
+                va0 = fmaT(x[t], w1[t], va0);
+                va1 = fmaT(x[t + 1], w1[t + 1], va1);
+            }
+            return va0 + va1;
         }
-        return va0 + va1;
     };
     auto next_stage = [&](int j) {   // block-uniform; returns the first staged row of stage j (this thread's window)
         __syncthreads();             // every thread is done with stage j-1: its buffer may be refilled
@@ -368,12 +379,15 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     // cut into few long chunks is latency-bound), but at least 4*S2 rows per chunk (each chunk re-reads S2-1 halo rows)
     const int64_t target = (int64_t)sep2d_num_sms() * ADS_PER_SM * ADS_WAVES_;
     const int chunks = (int)std::max<int64_t>(1, (target + a.tiles1 * nbatch - 1) / (a.tiles1 * nbatch));
-    int CR = std::max(std::max(8, 4 * S2), (a.m2 + chunks - 1) / chunks);
-    CR = std::min(CR, 1024);
-    a.tiles2 = (a.m2 + CR - 1) / CR;
-    int nrmax = 0;
-    rc = table_adjf_rows(t2, CR, st, &nrmax);
+    // (at least 4*S2 rows per chunk: each chunk re-reads S2-1 halo rows)
+    const int nchunks = std::max(1, std::min(chunks, a.m2 / std::max(8, 4 * S2)));
+    a.tiles2 = nchunks;
+    int CR = 0, nrmax = 0;
+    // chunks that must run the generic loop (array edges, irregular rates) are charged 30 % of a chunk, i.e. made
+    // shorter: all CTAs of the single wave then finish together
+    rc = table_chunk_plan(t2, nchunks, 0.3, st, &a.cstart, &CR, &nrmax);
     if (rc != LI_OK) return rc;
+    if (CR > 4096) return LI_OK;
     const int NRMAX = (std::max(nrmax, 1) + 1) & ~1;
     const size_t smem = ((size_t)ADS_NSTAGE * K * P1 + (size_t)NRMAX * S2) * sizeof(T) +
                         (size_t)((CR + 2 * S2 + 1) & ~1) * sizeof(int) + ADS_NSTAGE * sizeof(uint64_t);

@@ -614,6 +614,61 @@ int table_tile_rows(const li_table *t, int TD2, cudaStream_t st, const int32_t *
     return LI_OK;
 }
 
+int table_chunk_plan(const li_table *t, int nchunks, double penalty, cudaStream_t st, const int32_t **starts, int *crmax,
+                     int *nrmax)
+{
+    int rc = table_ensure_fold(t, st);
+    if (rc != LI_OK) return rc;
+    std::lock_guard<std::mutex> lock(t->mu);
+    auto it = t->chunk_plans.find(nchunks);
+    if (it == t->chunk_plans.end()) {
+        const int m = (int)t->ncols, S = t->S;
+        std::vector<int32_t> bpf(m + S), irrp(m + 1, 0);
+        LI_CUDA(cudaMemcpyAsync(bpf.data(), t->bpf, (m + S) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (t->irrp) LI_CUDA(cudaMemcpyAsync(irrp.data(), t->irrp, (m + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        LI_CUDA(cudaStreamSynchronize(st));
+        // cost of a column: 1, plus `penalty` chunks' worth for the first column of every run of columns that force
+        // their chunk onto the generic loop (not fed by exactly reg_R rows, or next to the array edges)
+        const double base = (double)m / nchunks;
+        std::vector<double> cost(m + 1, 0.0);
+        double total = 0.0;
+        bool prev = false;
+        for (int v = 0; v < m; ++v) {
+            const bool odd = !t->irrp || irrp[v + 1] != irrp[v] || v < S || v >= m - S;
+            total += 1.0 + ((odd && !prev) ? penalty * base : 0.0);
+            cost[v + 1] = total;
+            prev = odd;
+        }
+        std::vector<int32_t> b(nchunks + 1, 0);
+        int v = 0;
+        for (int k = 1; k < nchunks; ++k) {
+            const double want = total * k / nchunks;
+            while (v < m && cost[v] < want) ++v;
+            b[k] = std::max(v, b[k - 1]);
+        }
+        b[nchunks] = m;
+        li_table::ChunkPlan plan;
+        for (int k = 0; k < nchunks; ++k) {
+            const int va = b[k], vb = b[k + 1];
+            plan.crmax = std::max(plan.crmax, vb - va);
+            if (vb > va) plan.nrmax = std::max(plan.nrmax, (int)(bpf[vb - 1 + S] - bpf[va]));
+        }
+        LI_CUDA(cudaMalloc(&plan.starts, (nchunks + 1) * sizeof(int32_t)));
+        cudaError_t e = cudaMemcpyAsync(plan.starts, b.data(), (nchunks + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            cudaFree(plan.starts);
+            set_error("chunk plan upload failed: %s", cudaGetErrorString(e));
+            return LI_ERR_CUDA;
+        }
+        it = t->chunk_plans.emplace(nchunks, plan).first;
+    }
+    *starts = it->second.starts;
+    *crmax = it->second.crmax;
+    *nrmax = it->second.nrmax;
+    return LI_OK;
+}
+
 }  // namespace li
 
 // ---------------------------------------------------------------------------
@@ -741,6 +796,7 @@ int li_table_destroy(li_table *t)
     cudaFree(t->bpf);
     cudaFree(t->irrp);
     for (auto &kv : t->tile_rows) cudaFree(kv.second.first);
+    for (auto &kv : t->chunk_plans) cudaFree(kv.second.starts);
     delete t;
     return LI_OK;
 }
