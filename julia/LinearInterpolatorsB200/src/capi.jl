@@ -117,3 +117,34 @@ function tab_apply!(adjoint::Bool, t::Table, npre::Integer, npost::Integer, α::
     end
     return dst
 end
+
+# One Julia process per GPU (INTEGRATION.md, "Multi-GPU"): select the device before creating tables / arrays.
+set_device(dev::Integer) = check(ccall((:li_set_device, LIB), Cint, (Cint,), dev))
+function device_count()
+    n = Ref{Cint}(0)
+    check(ccall((:li_device_count, LIB), Cint, (Ptr{Cint},), n))
+    return Int(n[])
+end
+
+"""
+    Table(J, W, ncols)
+
+adopt index / weight tables computed in Julia (user-defined kernels: anything `getcoefs` can produce), reference
+layout `J::Matrix{Int}` 1-based and `W::Matrix{T}`, both `S x nrows`.  The bound check of `__fullcheck`
+(src/tabulated.jl:206-215) is done once here, on the device, instead of at every `apply!`.
+"""
+function Table(J::Matrix{Int}, W::Matrix{T}, ncols::Integer) where {T<:Floats}
+    size(J) == size(W) || throw(DimensionMismatch("J and W must have the same size"))
+    S, nrows = size(J)
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:li_table_import, LIB), Cint,
+                (Cint, Cint, Int64, Int64, Ptr{Int64}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
+                li_dtype(T), S, nrows, ncols, J, W, C_NULL, ref))
+    return Table{T}(ref[], S, nrows, Int(ncols))
+end
+
+# vscale!(y, β) on a device array (β = 0: zero-fill without reading y, like LazyAlgebra's vscale!)
+function vscale!(y::DeviceArray{T}, β::Real) where {T<:Floats}
+    check(ccall((:li_vscale, LIB), Cint, (Cint, Ptr{Cvoid}, Int64, Cdouble, Ptr{Cvoid}), li_dtype(T), y.ptr, length(y), β, C_NULL))
+    return y
+end

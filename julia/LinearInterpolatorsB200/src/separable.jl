@@ -52,3 +52,31 @@ function sep_apply!(α::Real, ::Type{P}, As::Tuple{Vararg{PerDim}}, x::HostOrDev
     end
     return y
 end
+
+"""
+    sep_accumulate!(P, ops, α, xs, β, y)
+
+`y <- β*y + α * Σ_k P(H_k) * xs[k]` for separable operators `H_k = A1_k*A2_k*...` (tuples of table-backed factors)
+acting on device arrays, in ONE library call (`li_sep_apply_batch`): the inner loop of an iterative fit,
+`m += H_k' * y_k` over the observed frames.  With β = 1 long batches run on several internal streams and are summed
+in a fixed order (deterministic).  β is applied by the first apply only.
+"""
+function sep_accumulate!(::Type{P}, ops::AbstractVector, α::Real, xs::AbstractVector{<:DeviceArray},
+                         β::Real, y::DeviceArray) where {P<:Operations}
+    n = length(ops)
+    n == length(xs) || throw(DimensionMismatch("one source array per operator"))
+    n == 0 && return y
+    N = length(ops[1])
+    handles = Ptr{Cvoid}[f.table.handle for op in ops for f in op]
+    srcs = Ptr{Cvoid}[x.ptr for x in xs]
+    dsts = fill(y.ptr, n)
+    β == 1 || vscale!(y, β)     # li_sep_apply_batch applies its beta at every apply: scale once, then accumulate
+    GC.@preserve ops xs y begin
+        check(ccall((:li_sep_apply_batch, LIB), Cint,
+                    (Cint, Cint, Int64, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Int64, Cdouble, Ptr{Ptr{Cvoid}}, Cdouble,
+                     Ptr{Ptr{Cvoid}}, Cint, Ptr{Cvoid}),
+                    P === Adjoint, N, n, handles, C_NULL, 1, α, srcs, 1.0, dsts, 0, C_NULL))
+        check(ccall((:li_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+    end
+    return y
+end
