@@ -10,6 +10,8 @@
 // they gather through L1/L2.  Windowed tables of separable operators take the fused, staged
 // kernels of li_sep2d.cu instead.  Threads always run along the contiguous dimension (the
 // opposite of the reference's CPU loop nest, which puts the interpolated index innermost).
+#include <cstdlib>
+
 #include "li_common.cuh"
 
 namespace li {
@@ -141,6 +143,156 @@ tab_adjoint_gather_dn_kernel(const int32_t *__restrict__ colptr, const int32_t *
     }
 }
 
+// ---- Streaming kernels for a strided dimension (npre > 1) of a windowed, monotone table ------------------------
+// Along a dimension other than the first the threads share nothing: a thread owns V consecutive elements of the
+// contiguous index (one 16-byte vector) and walks along the interpolated dimension with the window in registers,
+// so every src element is read once per chunk (plus S-1 halo planes) and every dst element written once, with
+// 16-byte coalesced accesses.  Same scheme as dim 2 of the fused kernels in li_sep2d.cu.
+template <typename T, int V>
+struct VecN {
+    T v[V];
+};
+template <typename T, int V>
+__device__ __forceinline__ VecN<T, V> ldv(const T *p)
+{
+    VecN<T, V> r;
+    if constexpr (sizeof(T) * V == 16)
+        *reinterpret_cast<uint4 *>(r.v) = *reinterpret_cast<const uint4 *>(p);
+    else
+        *reinterpret_cast<uint2 *>(r.v) = *reinterpret_cast<const uint2 *>(p);
+    return r;
+}
+template <typename T, int V>
+__device__ __forceinline__ void stv(T *p, const VecN<T, V> &r)
+{
+    if constexpr (sizeof(T) * V == 16)
+        *reinterpret_cast<uint4 *>(p) = *reinterpret_cast<const uint4 *>(r.v);
+    else
+        *reinterpret_cast<uint2 *>(p) = *reinterpret_cast<const uint2 *>(r.v);
+}
+__device__ __forceinline__ int clampi_(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+
+// Direct: the src planes base[i0] .. base[i1-1]+S-1 of the chunk stream through a window of S vectors whose rotation
+// is static (the plane loop is unrolled by S); after plane r every row whose window ends at r is emitted.
+// Flat / SafeFlat clamping = the plane index is clamped when loading (replicated edge planes).
+template <typename T, int S, int V>
+__global__ void __launch_bounds__(256)
+tab_direct_stream_kernel(const int32_t *__restrict__ base, const T *__restrict__ W, int nrows, int ncols, int64_t npv,
+                         int64_t npost, int CR, T alpha, T beta, const T *__restrict__ src, T *__restrict__ dst)
+{
+    const int64_t pv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pv >= npv) return;
+    const int i0 = blockIdx.y * CR, i1 = min(i0 + CR, nrows);
+    const int lo = base[i0], hi = base[i1 - 1] + S - 1;
+    const int64_t npre = npv * V;
+    for (int64_t q = blockIdx.z; q < npost; q += gridDim.z) {
+        const T *sp = src + pv * V + q * npre * ncols;
+        T *dp = dst + pv * V + (q * nrows + i0) * npre;
+        VecN<T, V> h[S];
+        int i = i0;
+        for (int r0 = lo; r0 <= hi; r0 += S) {
+#pragma unroll
+            for (int u = 0; u < S; ++u) {
+                const int r = r0 + u;
+                if (r <= hi) {   // block-uniform
+                    h[u] = ldv<T, V>(sp + (int64_t)clampi_(r, ncols - 1) * npre);
+                    while (i < i1 && base[i] + S - 1 == r) {   // rows completed by plane r (block-uniform)
+                        VecN<T, V> o;
+#pragma unroll
+                        for (int e = 0; e < V; ++e) o.v[e] = (T)0;
+#pragma unroll
+                        for (int t = 0; t < S; ++t) {
+                            const T w = W[(int64_t)i * S + t];
+#pragma unroll
+                            for (int e = 0; e < V; ++e) o.v[e] = fma_(h[(u + 1 + t) % S].v[e], w, o.v[e]);
+                        }
+                        if (beta == (T)0) {   // dst is never read
+#pragma unroll
+                            for (int e = 0; e < V; ++e) o.v[e] = alpha == (T)1 ? o.v[e] : alpha * o.v[e];
+                        } else {
+                            const VecN<T, V> d = ldv<T, V>(dp);
+#pragma unroll
+                            for (int e = 0; e < V; ++e) o.v[e] = fma_(alpha, o.v[e], beta * d.v[e]);
+                        }
+                        stv<T, V>(dp, o);
+                        dp += npre;
+                        ++i;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Adjoint (gather form, deterministic): the src rows feeding the chunk of dst planes [va, vb) stream in ascending
+// order; S accumulators hold the dst planes v .. v+S-1 (static rotation); dst plane v is complete once every row
+// whose folded window starts at v has been added -- ascending (row, tap) order, the order of the reference's
+// sequential scatter.  Clamped taps use the folded weights of the table (li_table.cu: fold_kernel); slots that no
+// tap of an edge row lands on are skipped, not multiplied by zero.
+template <typename T, int S, int V>
+__global__ void __launch_bounds__(256)
+tab_adjoint_stream_kernel(const int32_t *__restrict__ base, const int32_t *__restrict__ bpf, const T *__restrict__ Wf,
+                          int nrows, int ncols, int64_t npv, int64_t npost, int CR, T alpha, T beta,
+                          const T *__restrict__ src, T *__restrict__ dst)
+{
+    const int64_t pv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pv >= npv) return;
+    const int va = blockIdx.y * CR, vb = min(va + CR, ncols);
+    const int64_t npre = npv * V;
+    for (int64_t q = blockIdx.z; q < npost; q += gridDim.z) {
+        int i = bpf[va];                                   // first row with folded base >= va-(S-1)
+        const T *sp = src + pv * V + (q * nrows + i) * npre;
+        T *dp = dst + pv * V + (q * ncols + va) * npre;
+        VecN<T, V> acc[S];
+#pragma unroll
+        for (int t = 0; t < S; ++t)
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[t].v[e] = (T)0;
+        for (int v0 = va - (S - 1); v0 < vb; v0 += S) {
+#pragma unroll
+            for (int u = 0; u < S; ++u) {
+                const int vv = v0 + u;
+                if (vv < vb) {   // block-uniform
+                    const int iend = bpf[vv + S];          // rows with folded base <= vv end here
+                    const bool interior = vv > 0 && vv < ncols - S;
+                    for (; i < iend; ++i) {
+                        const VecN<T, V> y = ldv<T, V>(sp);
+                        sp += npre;
+                        int slo = 0, shi = S - 1;
+                        if (!interior) {   // first / last window of the array: only the slots the clamped taps land on
+                            const int b = base[i];
+                            slo = clampi_(b, ncols - 1) - vv, shi = clampi_(b + S - 1, ncols - 1) - vv;
+                        }
+#pragma unroll
+                        for (int t = 0; t < S; ++t) {
+                            if (t >= slo && t <= shi) {
+                                const T w = Wf[(int64_t)i * S + t];
+#pragma unroll
+                                for (int e = 0; e < V; ++e) {
+                                    const T x = alpha == (T)1 ? y.v[e] : alpha * y.v[e];
+                                    acc[(u + t) % S].v[e] = fma_(w, x, acc[(u + t) % S].v[e]);
+                                }
+                            }
+                        }
+                    }
+                    if (vv >= va) {   // dst plane vv is complete
+                        VecN<T, V> o = acc[u];
+                        if (beta != (T)0) {
+                            const VecN<T, V> d = ldv<T, V>(dp);
+#pragma unroll
+                            for (int e = 0; e < V; ++e) o.v[e] = fma_(beta, d.v[e], o.v[e]);
+                        }
+                        stv<T, V>(dp, o);
+                        dp += npre;
+                    }
+#pragma unroll
+                    for (int e = 0; e < V; ++e) acc[u].v[e] = (T)0;
+                }
+            }
+        }
+    }
+}
+
 // ---- Adjoint, atomic scatter (benchmarked variant; not run-to-run deterministic) ----
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -161,6 +313,27 @@ tab_adjoint_atomic_kernel(const int32_t *__restrict__ J, const T *__restrict__ W
     }
 }
 
+// the streaming kernels need a windowed monotone table with a compile-time S and 16-byte aligned vectors of V elements
+template <typename T, int SC>
+static bool stream_ok(const li_table *t, int64_t npre, const void *src, const void *dst)
+{
+    constexpr int V = 16 / (int)sizeof(T);
+    static const bool off = getenv("LI_B200_NO_STREAM_DN") != nullptr;
+    return SC > 0 && !off && t->windowed && t->monotone && npre % V == 0 && ((uintptr_t)src) % 16 == 0 &&
+           ((uintptr_t)dst) % 16 == 0;
+}
+
+// chunks along the interpolated dimension: enough CTAs to fill the machine (about 8 per SM with the other two grid
+// dimensions), but at least 8*S planes per chunk (each chunk re-reads S-1 halo planes)
+static void stream_chunks(int n, int64_t other_ctas, int S, int *CR, int *chunks)
+{
+    const int64_t want = (148 * 8 + other_ctas - 1) / std::max<int64_t>(other_ctas, 1);
+    int c = (int)std::max<int64_t>(1, std::min<int64_t>(want, n / std::max(8 * std::max(S, 1), 1)));
+    c = std::max(1, std::min(c, 65535));
+    *CR = (n + c - 1) / c;
+    *chunks = (n + *CR - 1) / *CR;
+}
+
 // ---------------------------------------------------------------------------
 template <typename T, int SC>
 static int launch_direct(const li_table *t, int64_t npre, int64_t npost, T alpha, T beta, const T *src, T *dst,
@@ -171,6 +344,16 @@ static int launch_direct(const li_table *t, int64_t npre, int64_t npost, T alpha
         dim3 grid((nrows + 255) / 256, (unsigned)std::min<int64_t>(npost, 65535));
         tab_direct_d1_kernel<T, SC><<<grid, 256, 0, st>>>(t->J, (const T *)t->W, t->S, nrows, ncols, npost, alpha,
                                                          beta, src, dst);
+    } else if (stream_ok<T, SC>(t, npre, src, dst)) {
+        constexpr int V = 16 / (int)sizeof(T);
+        const int64_t npv = npre / V;
+        const int threads = npv >= 256 ? 256 : (npv >= 128 ? 128 : (npv >= 64 ? 64 : 32));
+        const unsigned gx = (unsigned)((npv + threads - 1) / threads);
+        int CR, chunks;
+        stream_chunks(nrows, (int64_t)gx * std::min<int64_t>(npost, 65535), SC, &CR, &chunks);
+        dim3 grid(gx, chunks, (unsigned)std::min<int64_t>(npost, 65535));
+        tab_direct_stream_kernel<T, (SC ? SC : 1), V><<<grid, threads, 0, st>>>(t->base, (const T *)t->W, nrows, ncols, npv,
+                                                                              npost, CR, alpha, beta, src, dst);
     } else {
         constexpr int RB = 4;
         const int threads = npre >= 256 ? 256 : (npre >= 128 ? 128 : (npre >= 64 ? 64 : 32));
@@ -199,6 +382,29 @@ static int direct_T(const li_table *t, int64_t npre, int64_t npost, double alpha
     }
 }
 
+template <typename T, int S>
+static int launch_adjoint_stream(const li_table *t, int64_t npre, int64_t npost, T alpha, T beta, const T *src, T *dst,
+                                 cudaStream_t st, bool *done)
+{
+    *done = false;
+    if (!stream_ok<T, S>(t, npre, src, dst)) return LI_OK;
+    int rc = table_ensure_fold(t, st);
+    if (rc != LI_OK) return rc;
+    constexpr int V = 16 / (int)sizeof(T);
+    const int nrows = (int)t->nrows, ncols = (int)t->ncols;
+    const int64_t npv = npre / V;
+    const int threads = npv >= 256 ? 256 : (npv >= 128 ? 128 : (npv >= 64 ? 64 : 32));
+    const unsigned gx = (unsigned)((npv + threads - 1) / threads);
+    int CR, chunks;
+    stream_chunks(ncols, (int64_t)gx * std::min<int64_t>(npost, 65535), S, &CR, &chunks);
+    dim3 grid(gx, chunks, (unsigned)std::min<int64_t>(npost, 65535));
+    tab_adjoint_stream_kernel<T, S, V><<<grid, threads, 0, st>>>(t->base, t->bpf, (const T *)t->Wfold, nrows, ncols, npv, npost,
+                                                               CR, alpha, beta, src, dst);
+    LI_CHECK_LAUNCH();
+    *done = true;
+    return LI_OK;
+}
+
 template <typename T>
 static int adjoint_T(const li_table *t, int64_t npre, int64_t npost, double alpha, double beta, const void *src,
                      void *dst, int variant, cudaStream_t st)
@@ -214,6 +420,21 @@ static int adjoint_T(const li_table *t, int64_t npre, int64_t npost, double alph
                                                             a, (const T *)src, (T *)dst);
         LI_CHECK_LAUNCH();
         return LI_OK;
+    }
+    // strided dimension of a windowed monotone table: streaming gather (no transposed table needed)
+    if (npre > 1 && ncols >= t->S) {
+        bool done = false;
+        int rcs = LI_OK;
+        switch (t->S) {
+#define LI_ADJS(SS)                                                                                            \
+    case SS:                                                                                                   \
+        rcs = launch_adjoint_stream<T, SS>(t, npre, npost, a, b, (const T *)src, (T *)dst, st, &done);          \
+        break;
+            LI_ADJS(1) LI_ADJS(2) LI_ADJS(3) LI_ADJS(4) LI_ADJS(6) LI_ADJS(8)
+#undef LI_ADJS
+        default: break;
+        }
+        if (rcs != LI_OK || done) return rcs;
     }
     int rc = table_ensure_csc(t, st);
     if (rc != LI_OK) return rc;
