@@ -92,6 +92,13 @@ static int sep_apply_impl(int adjoint, int ndim, const li_table *const *tabs, co
         if (rc != LI_OK || done) return rc;
     }
 
+    // ... also when a third, untouched dimension follows: it is one more batch dimension
+    if (ndim == 3 && tabs[0] && tabs[1] && !tabs[2] && variant != LI_VARIANT_ATOMIC) {
+        bool done = false;
+        rc = sep2d_fused_apply(adjoint, tabs[0], tabs[1], dims_other[2] * nbatch, alpha, src, beta, dst, st, &done);
+        if (rc != LI_OK || done) return rc;
+    }
+
     size_t need = 0, half = 0;
     sep_workspace(plan, dtype, &need, &half);
     LI_REQUIRE(workspace_bytes >= need && (need == 0 || workspace), LI_ERR_ARG,

@@ -196,6 +196,70 @@ def test_tab_apply_nd(li, T, device):
                 A.variant = li.VARIANT_AUTO
 
 
+@pytest.mark.parametrize("T", DTYPES)
+@pytest.mark.parametrize("style", ["aligned", "overhang", "down", "up2"])
+def test_tab_apply_strided_streaming(li, T, style):
+    """Strided dimensions of sorted (windowed, monotone) tables with 16-byte aligned planes take the streaming
+    kernels (register window, vector loads): every kernel size, clamped edges, alpha / beta, non-finite samples."""
+    rng = np.random.default_rng(17)
+    shape = (36, 20, 8)
+    for entry in (KERNELS[0], KERNELS[1], KERNELS[2], KERNELS[4], KERNELS[9], KERNELS[10]):
+        for cname, cond in CONDITIONS:
+            for d in (2, 3):
+                ncols = shape[d - 1]
+                nrows = {"aligned": 2 * ncols, "overhang": 33, "down": max(3, ncols // 3), "up2": 2 * ncols + 1}[style]
+                xs = {"aligned": np.linspace(1, ncols, nrows), "overhang": np.linspace(-7.5, ncols + 9.25, nrows),
+                      "down": np.linspace(1, ncols, nrows), "up2": 0.3 + 0.5 * np.arange(nrows)}[style]
+                J, W = O.maketable(oracle_kernel(entry, cond), xs.astype(T), ncols, T)
+                A = li.TabulatedInterpolator(T, d, product_kernel(li, entry, cond, T), xs, ncols)
+                src = np.asfortranarray(rng.standard_normal(shape).astype(T))
+                oshape = tuple(nrows if i == d - 1 else n for i, n in enumerate(shape))
+                for alpha, beta in ((1, 0), (-1.5, 0.5)):
+                    d0 = np.asfortranarray(rng.standard_normal(oshape).astype(T))
+                    ref = O.tab_direct(J, W, ncols, d, src, alpha, beta, d0.copy(order="F"))
+                    dy = li.to_device(d0)
+                    li.apply_b(alpha, li.Direct, A, li.to_device(src), False, beta, dy)
+                    assert_close(li.to_host(dy), ref, T, factor=4)
+                    ysrc = np.asfortranarray(rng.standard_normal(oshape).astype(T))
+                    c0 = np.asfortranarray(rng.standard_normal(shape).astype(T))
+                    refa = O.tab_adjoint(J, W, ncols, d, ysrc, alpha, beta, c0.copy(order="F"))
+                    dd = li.to_device(c0)
+                    li.apply_b(alpha, li.Adjoint, A, li.to_device(ysrc), False, beta, dd)
+                    assert_close(li.to_host(dd), refa, T, scale=float(np.max(np.abs(refa))) + 1, factor=16)
+                # a non-finite sample reaches exactly the reference's footprint (no 0 * Inf from folded windows)
+                ybad = np.asfortranarray(rng.standard_normal(oshape).astype(T))
+                idx = [1, 2, 3]
+                for pos in (0, nrows // 2, nrows - 1):
+                    idx[d - 1] = pos
+                    ybad[tuple(idx)] = np.inf
+                refb = O.tab_adjoint(J, W, ncols, d, ybad, skip_zero=False)
+                gotb = li.to_host(A.adj * li.to_device(ybad))
+                if not np.isnan(W).any():
+                    assert np.array_equal(np.isfinite(gotb), np.isfinite(refb))
+
+
+def test_two_factors_on_3d_array_use_fused_kernels(li):
+    # H = A1*A2 applied to a 3-D array: the third dimension is one more batch dimension of the fused 2-D kernels
+    T = np.float32
+    rng = np.random.default_rng(3)
+    m, n, nz = (40, 30), (80, 60), 5
+    ker = li.LanczosKernel(T, 4)
+    x1, x2 = np.linspace(1, m[0], n[0]), np.linspace(1, m[1], n[1])
+    A1, A2 = li.TabulatedInterpolator(T, 1, ker, x1, m[0]), li.TabulatedInterpolator(T, 2, ker, x2, m[1])
+    J1, W1 = O.maketable(O.kernel(O.LANCZOS, 4), x1.astype(T), m[0], T)
+    J2, W2 = O.maketable(O.kernel(O.LANCZOS, 4), x2.astype(T), m[1], T)
+    src = np.asfortranarray(rng.standard_normal(m + (nz,)).astype(T))
+    ref = O.tab_direct(J1, W1, m[0], 1, O.tab_direct(J2, W2, m[1], 2, src))
+    dsrc = li.to_device(src)
+    (A1 * A2) * dsrc                            # (first use: one-off table analysis kernels)
+    n0 = li.launch_count()
+    out = (A1 * A2) * dsrc
+    assert li.launch_count() - n0 == 1          # one fused launch, not two passes
+    assert_close(li.to_host(out), ref, T, factor=8)
+    refa = O.tab_adjoint(J2, W2, m[1], 2, O.tab_adjoint(J1, W1, m[0], 1, ref))
+    assert_close(li.to_host((A1 * A2).adj * out), refa, T, factor=64)
+
+
 def test_beta_zero_never_reads_dst(li):
     T = np.float32
     A = li.TabulatedInterpolator(T, li.CatmullRomSpline(T), np.linspace(1, 9, 33), 9)
