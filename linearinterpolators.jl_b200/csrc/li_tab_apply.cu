@@ -293,6 +293,40 @@ tab_adjoint_stream_kernel(const int32_t *__restrict__ base, const int32_t *__res
     }
 }
 
+// ---- Adjoint along the contiguous dimension (npre == 1) of a windowed, monotone table -------------------------
+// thread <-> dst column j; the rows feeding it are the contiguous range [rowstart[j], rowstart[j+S]) (plus every row
+// hanging over the edge for the first / last column), row i contributes its tap j - base[i]: no transposed table, no
+// per-entry indirection, ascending (row, tap) order like the reference's sequential scatter.  Adjacent threads read
+// overlapping ranges of src (L1 hits), dst is written coalesced.
+template <typename T, int S>
+__global__ void __launch_bounds__(256)
+tab_adjoint_window_d1_kernel(const int32_t *__restrict__ base, const int32_t *__restrict__ rowstart, const T *__restrict__ W,
+                             int nrows, int ncols, int64_t npost, T alpha, T beta, const T *__restrict__ src,
+                             T *__restrict__ dst)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    const int e0 = j == 0 ? 0 : rowstart[j], e1 = j == ncols - 1 ? nrows : rowstart[j + S];
+    const bool edge = j == 0 || j == ncols - 1;
+    for (int64_t q = blockIdx.y; q < npost; q += gridDim.y) {
+        const T *sp = src + q * nrows;
+        T *d = dst + q * ncols + j;
+        T acc = beta == (T)0 ? (T)0 : beta * (*d);
+        for (int i = e0; i < e1; ++i) {
+            const T x = alpha == (T)1 ? sp[i] : alpha * sp[i];
+            const int b = base[i];
+            if (!edge) {
+                acc = fma_(W[(int64_t)i * S + (j - b)], x, acc);
+            } else {   // every tap of the row that clamps onto this column, in tap order
+#pragma unroll
+                for (int t = 0; t < S; ++t)
+                    if (clampi_(b + t, ncols - 1) == j) acc = fma_(W[(int64_t)i * S + t], x, acc);
+            }
+        }
+        *d = acc;
+    }
+}
+
 // ---- Adjoint, atomic scatter (benchmarked variant; not run-to-run deterministic) ----
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -435,6 +469,27 @@ static int adjoint_T(const li_table *t, int64_t npre, int64_t npost, double alph
         default: break;
         }
         if (rcs != LI_OK || done) return rcs;
+    }
+    // contiguous dimension of a windowed monotone table: gather over the row ranges of the window table
+    if (npre == 1 && t->windowed && t->monotone && ncols >= 2 && !getenv("LI_B200_NO_STREAM_DN")) {
+        int rcw = table_ensure_rowstart(t, st);
+        if (rcw != LI_OK) return rcw;
+        dim3 grid((ncols + 255) / 256, (unsigned)std::min<int64_t>(npost, 65535));
+        bool launched = true;
+        switch (t->S) {
+#define LI_ADJW(SS)                                                                                                  \
+    case SS:                                                                                                         \
+        tab_adjoint_window_d1_kernel<T, SS><<<grid, 256, 0, st>>>(t->base, t->rowstart, (const T *)t->W, nrows, ncols, npost, \
+                                                                 a, b, (const T *)src, (T *)dst);                    \
+        break;
+            LI_ADJW(1) LI_ADJW(2) LI_ADJW(3) LI_ADJW(4) LI_ADJW(6) LI_ADJW(8)
+#undef LI_ADJW
+        default: launched = false; break;
+        }
+        if (launched) {
+            LI_CHECK_LAUNCH();
+            return LI_OK;
+        }
     }
     int rc = table_ensure_csc(t, st);
     if (rc != LI_OK) return rc;
