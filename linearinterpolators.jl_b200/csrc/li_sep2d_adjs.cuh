@@ -56,7 +56,7 @@ constexpr int ADS_PER_SM = ADS_OCC_ * 256 / ADS_NT;   // CTAs per SM of the 4-by
 
 template <int S2>
 struct AdsK {   // src rows per stage: a multiple of 2*S2 so that the static schedule has whole slot rotations
-    static constexpr int value = S2 == 6 ? 12 : ADS_K_;
+    static constexpr int value = (S2 == 6 || S2 == 3) ? 12 : ADS_K_;
 };
 
 template <typename T, int S1, int S2, int NU, int R>
@@ -421,7 +421,7 @@ int sep2d_adj_stream(SepArgs<T> &a, const li_table *t1, const li_table *t2, int6
 #ifdef LI_DEV_FAST   // development builds: the headline pair only
     LI_SEP(4, 4)
 #else
-    LI_SEP(2, 2) LI_SEP(4, 4) LI_SEP(6, 6) LI_SEP(2, 4) LI_SEP(4, 2) LI_SEP(4, 6) LI_SEP(6, 4)
+    LI_SEP(2, 2) LI_SEP(4, 4) LI_SEP(6, 6) LI_SEP(2, 4) LI_SEP(4, 2) LI_SEP(4, 6) LI_SEP(6, 4) LI_SEP(3, 3)
 #endif
 #undef LI_SEP
     return LI_OK;
