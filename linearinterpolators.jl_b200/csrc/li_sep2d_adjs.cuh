@@ -142,21 +142,31 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
             }
         }
     }
-    // the usual tap pattern: only the first and the last two staged values can be padding; they are cleared with
-    // bit masks (one LOP3 each).  Warps holding any other pattern (array edges) take the copy with selects.
-    constexpr unsigned MID = ((1u << (NU - 2)) - 1u) & ~1u;
+    // Padding of the staged window is cleared with bit masks (one LOP3 per masked position).  Level 1, the pattern of
+    // an integer up-sampling rate: only the first and the last two values can be padding (3 masks, static loop).
+    // Level 2, any rate: the first and the last NTAIL values (generic loop).  Warps holding any other pattern (array
+    // edges) take the copy with a select per tap (level 0).
+    constexpr int NTAIL = NU <= 6 ? NU - 1 : NU / 2;
+    constexpr unsigned MID = ((1u << (NU - 2)) - 1u) & ~1u, MID2 = ((1u << (NU - NTAIL)) - 1u) & ~1u;
     const bool warp_clean = __all_sync(0xffffffffu, (vm & MID) == MID);
+    const bool warp_clean2 = __all_sync(0xffffffffu, (vm & MID2) == MID2);
     using Bits = typename std::conditional<sizeof(T) == 4, uint32_t, uint64_t>::type;
     Bits k0 = (vm & 1u) ? ~(Bits)0 : (Bits)0;
-    Bits ka = ((vm >> (NU - 2)) & 1u) ? ~(Bits)0 : (Bits)0;
-    Bits kb = ((vm >> (NU - 1)) & 1u) ? ~(Bits)0 : (Bits)0;
+    Bits kt[NTAIL];
+#pragma unroll
+    for (int t = 0; t < NTAIL; ++t) kt[t] = ((vm >> (NU - NTAIL + t)) & 1u) ? ~(Bits)0 : (Bits)0;
     int rowstep = P1;
     int dstep = a.m1;
     // (opaque to the optimiser: otherwise the masks turn back into compare + select pairs and vm into NU flags)
-    if constexpr (sizeof(T) == 4)
-        asm volatile("" : "+r"(k0), "+r"(ka), "+r"(kb), "+r"(vm), "+r"(rowstep), "+r"(dstep));
-    else
-        asm volatile("" : "+l"(k0), "+l"(ka), "+l"(kb), "+r"(vm), "+r"(rowstep), "+r"(dstep));
+    if constexpr (sizeof(T) == 4) {
+        asm volatile("" : "+r"(k0), "+r"(vm), "+r"(rowstep), "+r"(dstep));
+#pragma unroll
+        for (int t = 0; t < NTAIL; ++t) asm volatile("" : "+r"(kt[t]));
+    } else {
+        asm volatile("" : "+l"(k0), "+r"(vm), "+r"(rowstep), "+r"(dstep));
+#pragma unroll
+        for (int t = 0; t < NTAIL; ++t) asm volatile("" : "+l"(kt[t]));
+    }
     auto keep = [](T x, Bits m) {
         Bits b;
         memcpy(&b, &x, sizeof b);
@@ -185,10 +195,14 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 #pragma unroll
             for (int e = 0; e < V; ++e) x[t + e] = q.v[e];
         }
-        if constexpr (decltype(clean)::value) {
+        if constexpr (decltype(clean)::value == 1) {
             x[0] = keep(x[0], k0);
-            x[NU - 2] = keep(x[NU - 2], ka);
-            x[NU - 1] = keep(x[NU - 1], kb);
+            x[NU - 2] = keep(x[NU - 2], kt[NTAIL - 2]);
+            x[NU - 1] = keep(x[NU - 1], kt[NTAIL - 1]);
+        } else if constexpr (decltype(clean)::value == 2) {
+            x[0] = keep(x[0], k0);
+#pragma unroll
+            for (int t = 0; t < NTAIL; ++t) x[NU - NTAIL + t] = keep(x[NU - NTAIL + t], kt[t]);
         } else {
             unsigned m = vm;
             asm volatile("" : "+r"(m));   // (keeps the NU bit tests out of registers)
@@ -229,17 +243,22 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
         oldv[(S2 - 1 + i) % S2] = (T)0;
         if (ld_old && va + i < vb) oldv[(S2 - 1 + i) % S2] = dp[(int64_t)i * dstep];   // (beta == 0: dst is never read)
     }
-    auto emit = [&](int vv, T value, int slot) {   // dst row vv is complete; slot = (vv - v0) % S2, static at every call
+    // (compiled once for beta == 0 and once for beta != 0: `hasbeta` is a compile-time tag)
+    auto emit = [&](int vv, T value, int slot, auto hasbeta) {   // dst row vv is complete; slot = (vv - v0) % S2, static
         if (vv >= va) {
-            const T o = beta ? fmaT(betav, oldv[slot], value) : value;
-            if (have) *dp = o;
-            if (ld_old && vv + S2 < vb) oldv[slot] = dp[(int64_t)S2 * dstep];
+            if constexpr (!decltype(hasbeta)::value) {   // dst is never read
+                if (have) *dp = value;
+            } else {
+                const T o = fmaT(betav, oldv[slot], value);
+                if (have) *dp = o;
+                if (ld_old && vv + S2 < vb) oldv[slot] = dp[(int64_t)S2 * dstep];
+            }
             dp += dstep;
         }
     };
 
     // ---- static schedule: stage j holds the R rows of each of the dst rows v0 + j*DR .. + DR-1
-    auto run_regular = [&](auto clean) {
+    auto run_regular = [&](auto clean, auto hasbeta) {
         if constexpr (R > 0) {
             constexpr int DR = K / R;
             const T *pw = sW2;
@@ -258,7 +277,7 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 #pragma unroll
                             for (int s = 0; s < S2; ++s) acc[(d + s) % S2] = fmaT(w2[s], val, acc[(d + s) % S2]);
                         }
-                        emit(vv, acc[d % S2], d % S2);
+                        emit(vv, acc[d % S2], d % S2, hasbeta);
                         acc[d % S2] = (T)0;
                     }
                 }
@@ -268,7 +287,7 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
     };
 
     // ---- generic schedule: for dst row vv, every src row whose folded window starts at vv
-    auto run_generic = [&](auto clean) {
+    auto run_generic = [&](auto clean, auto hasbeta) {
         const T *pw = sW2;
         const int *pn = sNv;
         const T *prow = sS + off;
@@ -317,7 +336,7 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
                                 if (s >= lo && s <= hi) acc[(u + s) % S2] = fmaT(w2[s], val, acc[(u + s) % S2]);
                         }
                     }
-                    emit(vv, acc[u], u);
+                    emit(vv, acc[u], u, hasbeta);
                     acc[u] = (T)0;
                 }
             }
@@ -326,17 +345,23 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
     };
 
     // (every copy runs the same sequence of barriers, so warps of one CTA may take different copies)
-    if (regular) {
-        if (warp_clean)
-            run_regular(std::true_type{});
-        else
-            run_regular(std::false_type{});
-    } else {
-        if (warp_clean)
-            run_generic(std::true_type{});
-        else
-            run_generic(std::false_type{});
-    }
+    auto run = [&](auto hasbeta) {
+        if (regular) {
+            if (warp_clean)
+                run_regular(std::integral_constant<int, 1>{}, hasbeta);
+            else
+                run_regular(std::integral_constant<int, 0>{}, hasbeta);
+        } else {
+            if (warp_clean2)
+                run_generic(std::integral_constant<int, 2>{}, hasbeta);
+            else
+                run_generic(std::integral_constant<int, 0>{}, hasbeta);
+        }
+    };
+    if (beta)
+        run(std::true_type{});
+    else
+        run(std::false_type{});
 }
 
 // ---------------------------------------------------------------------------------------------

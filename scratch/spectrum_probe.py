@@ -19,7 +19,9 @@ cases = [("Lanczos4 2x f32", np.float32, lambda T: li.LanczosKernel(T, 4), 4096,
          ("Lanczos4 1.5x f32", np.float32, lambda T: li.LanczosKernel(T, 4), 5464, 8192),
          ("Lanczos4 0.5x f32 (down)", np.float32, lambda T: li.LanczosKernel(T, 4), 8192, 4096),
          ("Quadratic 2x f32 (S=3: passes)", np.float32, lambda T: li.QuadraticSpline(T), 4096, 8192)]
+only = os.environ.get("ONLY")
 for name, T, mk, m, n in cases:
+    if only and only not in name: continue
     ker = mk(T)
     x = np.linspace(1.0, float(m), n)
     A1, A2 = li.TabulatedInterpolator(T, 1, ker, x, m), li.TabulatedInterpolator(T, 2, ker, x, m)
