@@ -60,11 +60,11 @@ struct AdsK {   // src rows per stage: a multiple of 2*S2 so that the static sch
 };
 
 template <typename T, int S1, int S2, int NU, int R>
-__global__ void __launch_bounds__(ADS_NT, (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? ADS_PER_SM : ADS_PER_SM / 2)
+__global__ void __launch_bounds__(ADS_NT, (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? ADS_PER_SM : (sizeof(T) == 4 ? 3 : 2))
 sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 {
     constexpr int NT = ADS_NT, K = AdsK<S2>::value, NSTAGE = ADS_NSTAGE;
-    constexpr int V = 8 / (int)sizeof(T);   // elements per 8-byte shared-memory load
+    constexpr int V = 2;   // elements per shared-memory load of the gather: LDS.64 for float, LDS.128 for double
     static_assert(NU % V == 0 && NU >= 4 && NU % 2 == 0, "bad NU");
     static_assert(R == 0 || (K % R == 0 && (K / R) % S2 == 0), "bad stage size");
 
@@ -380,7 +380,7 @@ static int launch_stream(SepArgs<T> &a, int CR, int NRMAX, size_t smem, int64_t 
 template <typename T, int S1, int S2>
 static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64_t nbatch, cudaStream_t st, bool *done)
 {
-    constexpr int V = 8 / (int)sizeof(T), AL = 16 / (int)sizeof(T), K = AdsK<S2>::value;
+    constexpr int V = 2, AL = 16 / (int)sizeof(T), K = AdsK<S2>::value;
     constexpr int NU_S = (S1 + 2 + 1) & ~1, NU_L = 2 * S1 + 2;   // taps kept per thread: same-rate / 2x operators
     if (a.m1 < S1 || a.m2 < S2) return LI_OK;                    // folding needs a full window inside the array
     if (a.n1 % AL != 0 || ((uintptr_t)a.src) % 16 != 0) return LI_OK;   // bulk copies need 16-byte aligned row segments
