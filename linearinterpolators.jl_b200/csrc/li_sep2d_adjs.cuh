@@ -60,7 +60,7 @@ struct AdsK {   // src rows per stage: a multiple of 2*S2 so that the static sch
 };
 
 template <typename T, int S1, int S2, int NU, int R>
-__global__ void __launch_bounds__(ADS_NT, (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? ADS_PER_SM : (sizeof(T) == 4 ? 3 : 2))
+__global__ void __launch_bounds__(ADS_NT, (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? ADS_PER_SM : ADS_PER_SM / 2)
 sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 {
     constexpr int NT = ADS_NT, K = AdsK<S2>::value, NSTAGE = ADS_NSTAGE;
