@@ -21,10 +21,10 @@ extern "C" int li_affine2d_apply(int adjoint, const li_kernel_desc *ker1, const 
                                  double alpha, const void *src_dev, double beta, void *dst_dev, int variant, int flags,
                                  void *stream)
 {
-    // variant: LI_VARIANT_AUTO = tiled kernels (shared-memory staging); LI_VARIANT_ATOMIC = one thread per pixel
-    // straight on global memory (the first implementation, kept for comparison)
-    const bool tiled = variant != LI_VARIANT_ATOMIC && !getenv("LI_B200_AFFINE_PLAIN") &&
-                       (!adjoint || getenv("LI_B200_AFFINE_TILED_ADJ"));
+    // direct: LI_VARIANT_AUTO = tiled kernel (source boxes staged in shared memory), LI_VARIANT_ATOMIC = one thread
+    // per pixel straight on global memory (the first implementation, kept for comparison); the adjoint is the
+    // atomic scatter in both cases
+    const bool tiled = !adjoint && variant != LI_VARIANT_ATOMIC && !getenv("LI_B200_AFFINE_PLAIN");
     LI_REQUIRE(ker1 && ker2 && R && dst_dev, LI_ERR_ARG, "null argument");
     LI_REQUIRE(ker1->dtype == ker2->dtype, LI_ERR_ARG, "kernels must share one floating-point type");
     LI_REQUIRE(n1 >= 0 && n2 >= 0 && m1 >= 1 && m2 >= 1 && nbatch >= 0, LI_ERR_DIM, "bad dimensions");

@@ -169,16 +169,15 @@ affine_adjoint_atomic_kernel(AffineArgs<T> a, const T *__restrict__ src, T *__re
 
 
 // ---------------------------------------------------------------------------------------------
-// Tiled variants.  A CTA owns a TX x TY tile of output pixels (PP pixels per thread); the coefficients of its
-// pixels are evaluated once and kept in registers for all images of the batch.  The clamped tap indices of the
-// tile are reduced to their bounding box in the source image, which is staged in shared memory image by image:
-//   direct : coalesced cp.async copies of the box (double buffered: image b+1 lands while image b is interpolated),
-//            then S1*S2 shared-memory loads per pixel instead of global ones;
-//   adjoint: the taps are accumulated into the (zeroed) box with shared-memory atomics and the box is flushed with
-//            one global atomic per touched element instead of S1*S2 per pixel.
-// The row pitch of the box is chosen on the host (mod 32) so that the lanes of a warp, which walk through the box
-// along the direction (R.xx, R.yx), fall into different banks.  Tiles whose box does not fit (extreme
-// magnification) take the per-pixel global path inside the same kernel.
+// Tiled forward.  A CTA owns a TX x TY tile of output pixels (PP pixels per thread); the coefficients of its pixels are
+// evaluated once and kept in registers for all images of the batch.  The clamped tap indices of the tile are reduced
+// to their bounding box in the source image, which is staged in shared memory image by image (one tensor-map TMA copy
+// per box, several images in flight; plain loads when the rows are not 16-byte aligned), then each pixel reads its
+// S1*S2 taps from shared memory instead of global memory.  The row pitch of the box is chosen on the host (mod 32) so
+// that the lanes of a warp, which walk through the box along the direction (R.xx, R.yx), fall into different banks.
+// Tiles whose box does not fit (extreme magnification) gather from global memory inside the same kernel.
+// (A shared-memory privatised ADJOINT of the same shape was measured at half the speed of the global atomics of
+// affine_adjoint_atomic_kernel -- float atomics on shared memory are CAS loops -- and was removed.)
 constexpr int AFT_TX = 32, AFT_TY = 32, AFT_NT = 512, AFT_PP = AFT_TX * AFT_TY / AFT_NT;
 constexpr int AFT_NSTG = 6;   // direct: boxes (images) in flight per CTA -- the per-image work of a tile is far shorter
                               // than a DRAM round trip, so the copies run several images ahead
@@ -190,7 +189,7 @@ struct TilePix {
     bool ok;      // inside the image and coefficients valid
 };
 
-template <typename T, int S1, int S2, bool ADJ>
+template <typename T, int S1, int S2>
 __global__ void __launch_bounds__(AFT_NT, 2)
 affine_tiled_kernel(AffineArgs<T> a, const T *__restrict__ src, T *__restrict__ dst, int *__restrict__ err,
                     const int pmod, const int cap /* elements per box buffer */,
@@ -257,8 +256,7 @@ affine_tiled_kernel(AffineArgs<T> a, const T *__restrict__ src, T *__restrict__ 
     const int P = bulk ? PB : BW + ((pmod - BW) & 31);
     const bool staged = bulk ? (BW <= PB && BH <= HB) : ((int64_t)P * BH <= cap);   // block-uniform
 
-    const int64_t splane = ADJ ? (int64_t)a.n1 * a.n2 : (int64_t)a.m1 * a.m2;   // planes of src / dst
-    const int64_t dplane = ADJ ? (int64_t)a.m1 * a.m2 : (int64_t)a.n1 * a.n2;
+    const int64_t splane = (int64_t)a.m1 * a.m2, dplane = (int64_t)a.n1 * a.n2;   // planes of src / dst
     const bool plain = a.alpha == (T)1 && a.beta == (T)0;
 
     // per pixel: offset of tap (0,0) in the box when no tap is clamped, else -1 (taps are clamped one by one)
@@ -273,7 +271,7 @@ affine_tiled_kernel(AffineArgs<T> a, const T *__restrict__ src, T *__restrict__ 
     };
     const int warp = tid >> 5, lane = tid & 31;
 
-    if constexpr (!ADJ) {
+    {
         // box of image b -> buffer k: ONE tensor-map TMA copy of the PB x HB box at (lo1, lo2, b) issued by thread 0
         // (elements outside the image are zero-filled and never read), or plain loads by everybody when the rows
         // of the image are not 16-byte aligned
@@ -383,42 +381,6 @@ affine_tiled_kernel(AffineArgs<T> a, const T *__restrict__ src, T *__restrict__ 
             }
             if (staged) __syncthreads();   // every thread is done with this buffer before it is refilled
         }
-    } else {
-        for (int64_t b = blockIdx.z; b < a.nbatch; b += gridDim.z) {
-            T *dp = dst + b * dplane;
-            if (staged) {
-                for (int k = tid; k < P * BH; k += NT) box[k] = (T)0;
-                __syncthreads();
-            }
-#pragma unroll
-            for (int p = 0; p < PP; ++p) {
-                if (!px[p].ok) continue;
-                T val = src[b * splane + (int64_t)(blockIdx.y * TY + ly + p * RY) * a.n1 + i1];
-                if (a.alpha != (T)1) val = a.alpha * val;
-#pragma unroll
-                for (int s2 = 0; s2 < S2; ++s2) {
-                    const T tmp = px[p].w2[s2] * val;   // :225-232
-#pragma unroll
-                    for (int s1 = 0; s1 < S1; ++s1) {
-                        const T t = px[p].w1[s1] * tmp;
-                        if (staged)
-                            atomicAdd(box + (off[p] >= 0 ? off[p] + s2 * P + s1 : tap_off(p, s1, s2)), t);
-                        else
-                            atomicAdd(dp + (int64_t)clampi(px[p].b2 + s2, a.m2 - 1) * a.m1 + clampi(px[p].b1 + s1, a.m1 - 1), t);
-                    }
-                }
-            }
-            if (staged) {
-                __syncthreads();
-                T *gp = dp + (int64_t)lo2 * a.m1 + lo1;
-                for (int r = warp; r < BH; r += NT / 32)
-                    for (int c = lane; c < BW; c += 32) {
-                        const T v = box[r * P + c];
-                        if (v != (T)0) atomicAdd(gp + (int64_t)r * a.m1 + c, v);   // (elements no tap landed on stay untouched)
-                    }
-                __syncthreads();
-            }
-        }
     }
 }
 
@@ -453,6 +415,9 @@ static int best_pitch_mod(double xx, double yx, int step = 1)
     return best;
 }
 
+template <typename T, int S1, int S2>
+static int launch_affine(int adjoint, const AffineArgs<T> &a, const T *src, T *dst, int *err, cudaStream_t st);
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -480,14 +445,7 @@ static int launch_affine_tiled(int adjoint, const AffineArgs<T> &a, const T *src
     grid.z = (unsigned)std::max<int64_t>(1, std::min<int64_t>(a.nbatch, (148 * 4 + tiles - 1) / tiles));
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
-    if (adjoint) {
-        const int cap = (int)(20 * 1024 / sizeof(T));
-        auto kern = affine_tiled_kernel<T, S1, S2, true>;
-        kern<<<grid, AFT_NT, (size_t)cap * sizeof(T), st>>>(a, src, dst, err, best_pitch_mod((double)a.xx, (double)a.yx), cap,
-                                                            0, 0, 0, tmap);
-        LI_CHECK_LAUNCH();
-        return LI_OK;
-    }
+    if (adjoint) return launch_affine<T, S1, S2>(adjoint, a, src, dst, err, st);   // (the adjoint has no tiled form)
     // direct: source box of a tile = extent of TX x TY pixels under the linear part of R, plus the taps
     const double ex = (AFT_TX - 1) * std::fabs((double)a.xx) + (AFT_TY - 1) * std::fabs((double)a.xy);
     const double ey = (AFT_TX - 1) * std::fabs((double)a.yx) + (AFT_TY - 1) * std::fabs((double)a.yy);
@@ -515,7 +473,7 @@ static int launch_affine_tiled(int adjoint, const AffineArgs<T> &a, const T *src
         }
     }
     const size_t smem = (size_t)cap * sizeof(T) * (bulk ? AFT_NSTG : 1);
-    auto kern = affine_tiled_kernel<T, S1, S2, false>;
+    auto kern = affine_tiled_kernel<T, S1, S2>;
     LI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
     kern<<<grid, AFT_NT, smem, st>>>(a, src, dst, err, pmod, cap, bulk, PB, HB, tmap);
     LI_CHECK_LAUNCH();
