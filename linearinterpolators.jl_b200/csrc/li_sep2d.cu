@@ -3,21 +3,18 @@
 // H = A1*A2 with A1 / A2 table-backed interpolators along dimensions 1 / 2 (reference: the
 // LazyAlgebra composition of test/benchmarks.jl:27-29, whose factors are the loops of
 // src/tabulated.jl:394-478 / src/sparse.jl:719-800; same mathematics as src/separable.jl:56-162).
-// The reference makes two full passes over memory with an intermediate array; here one CTA
-// produces one output tile from one input tile, the intermediate lives in shared memory, and each
-// element of src and dst crosses HBM once (plus tile halos, which hit in L2).
+// The reference makes two full passes over memory with an intermediate array; here each element of src and dst
+// crosses HBM once (plus a few halo rows per chunk).
 //
-// Both tables must be "windowed": row i reads columns clamp(base[i] + s, 0, ncols-1), s = 0..S-1,
-// which is what getcoefs (src/boundaries.jl:87-156) always produces.  The clamp is applied while
-// staging the input tile, so the inner loops use un-clamped contiguous windows.
+// Both tables must be "windowed" and monotone: row i reads columns clamp(base[i] + s, 0, ncols-1), s = 0..S-1, with
+// non-decreasing bases -- what getcoefs (src/boundaries.jl:87-156) produces for sorted positions.
 //
-//   forward : stage src tile (clamped) -> pass 1 along dim 1 (smem -> smem, per-thread taps in
-//             registers) -> pass 2 along dim 2 (threads along the contiguous dim, a sliding window of
-//             S2 rows in registers, block-uniform weights) -> coalesced vector stores.
-//   adjoint : the exact transpose: threads along the contiguous dim read y rows with coalesced vector
-//             loads and slide S2 accumulators along dim 2 (the reference's sequential scatter order),
-//             the dim-2 result goes to smem, then a gather along dim 1 with per-thread taps in registers
-//             writes the owned dst tile.  No atomics; the result is deterministic.
+//   forward : sep2d_fwd_kernel (this file): a streaming register pipeline fed by a ring of TMA bulk copies.
+//   adjoint : sep2d_adj_stream_kernel (li_sep2d_adjs.cuh): the same data flow run backwards; it is tried first and
+//             declines what it cannot stage.  The tile-owned kernels of this file (sep2d_adj_regular_kernel,
+//             sep2d_adj_kernel: dim-2 accumulation from global memory into a shared-memory intermediate, then a
+//             dim-1 gather) are the fallback for unaligned sources and for down-sampling along dim 1.
+//   No kernel uses atomics; every dst element is written once by its owner, in a fixed order (deterministic).
 #include <algorithm>
 
 #include "li_common.cuh"
