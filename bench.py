@@ -222,11 +222,42 @@ def run_b200(args):
     total_ms = evs[0][0].elapsed_time(evs[-1][2])
     fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     adj_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
-    ms_per_step = total_ms / args.steps
+    eager_ms_per_step = total_ms / args.steps
+
+    # The same K steps replayed from CUDA graphs (one captured step per buffer set): the two kernels of a step take
+    # ~140 us while Python needs ~85 us to issue them, so with 8 ranks sharing the host cores the eager loop can
+    # become host-bound; the graphs take the host out of the timed region.  Falls back to the eager time if the
+    # capture is refused.
+    ms_per_step, timed_how = eager_ms_per_step, "eager calls through the public API"
+    try:
+        graphs = []
+        cap_stream = torch.cuda.Stream(dev)
+        cap_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap_stream):
+            for b in range(NBUF):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap_stream):
+                    step(b)
+                graphs.append(g)
+        torch.cuda.current_stream(dev).wait_stream(cap_stream)
+        for k in range(4):
+            graphs[k % NBUF].replay()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for k in range(args.steps):
+            graphs[k % NBUF].replay()
+        g1.record()
+        barrier()
+        ms_per_step = g0.elapsed_time(g1) / args.steps
+        timed_how = "CUDA-graph replay of the public-API calls (one captured step per buffer set)"
+        launches = 2 * args.steps
+    except Exception as exc:  # pragma: no cover
+        timed_how += f" (graph capture refused: {type(exc).__name__})"
     if dist is not None:
-        t = torch.tensor([ms_per_step, fwd_ms, adj_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_per_step, fwd_ms, adj_ms, eager_ms_per_step], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step, fwd_ms, adj_ms = (float(v) for v in t.tolist())
+        ms_per_step, fwd_ms, adj_ms, eager_ms_per_step = (float(v) for v in t.tolist())
     value = world * SAMPLES_PER_STEP / (ms_per_step * 1e-3) / 1e9
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
@@ -306,6 +337,8 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "alpha": 1, "beta": 0, "images_per_gpu": 1,
                        "l2": "inputs rotate over 2 buffer sets of 671 MB each (> 126 MB L2); no timed kernel re-reads fresh data",
+                       "timed_region": timed_how, "eager_ms_per_step": eager_ms_per_step,
+                       "per_launch_times": "CUDA events around each apply in the eager pass of the same K steps",
                        "host_wall_ms_per_step": 1e3 * t_host / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
