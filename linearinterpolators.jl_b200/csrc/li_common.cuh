@@ -8,6 +8,7 @@
 #include <atomic>
 #include <mutex>
 #include <map>
+#include <vector>
 
 #include "li_b200.h"
 
@@ -83,7 +84,9 @@ struct li_table {
     struct ChunkPlan {
         int32_t *starts = nullptr;
         int crmax = 0, nrmax = 0;
+        std::vector<int32_t> starts_host, src_end_host;   // per chunk: first dst row; src rows needed (exclusive)
     };
+    mutable std::vector<int32_t> base_host;   // lazily: host copy of `base` (band planning of the host pipeline)
     mutable std::map<int, ChunkPlan> chunk_plans;
     // cached footprint bounds: key = tile rows G -> max over aligned tiles of (max base - min base)
     mutable std::map<int, int> fwd_span;
@@ -108,7 +111,8 @@ int table_tile_rows(const li_table *t, int TD2, cudaStream_t st, const int32_t *
 // fed by exactly reg_R rows (or touches a folded window) runs the slower generic loop and is made shorter by `penalty`
 // (fraction of a chunk).  *starts (device) has nchunks+1 boundaries.
 int table_chunk_plan(const li_table *t, int nchunks, double penalty, cudaStream_t st, const int32_t **starts, int *crmax,
-                     int *nrmax);
+                     int *nrmax, const li_table::ChunkPlan **plan = nullptr);
+int table_base_host(const li_table *t, cudaStream_t st, const std::vector<int32_t> **base);
 // builds a table from device positions into preallocated device arrays (used by the OTF operators)
 int table_create_impl(const li_kernel_desc *ker, const void *pos_dev, int64_t nrows, int64_t ncols,
                       cudaStream_t st, li_table **out);
@@ -117,6 +121,8 @@ int tab_apply_impl(int adjoint, const li_table *t, int64_t npre, int64_t npost, 
 int vscale_impl(int dtype, void *y, int64_t n, double beta, cudaStream_t st);
 int staging(int slot, size_t bytes, void **out, void *stream_key = nullptr);  // grow-only device scratch per (thread, stream)
 int sep2d_fused_supported(const li_table *t1, const li_table *t2);
+int sep2d_host_banded(int adjoint, const li_table *t1, const li_table *t2, double alpha, const void *src_host, void *dst_host,
+                      void *dsrc, void *ddst, cudaStream_t st, bool *done);
 int sep2d_fused_apply(int adjoint, const li_table *t1, const li_table *t2, int64_t nbatch,
                       double alpha, const void *src, double beta, void *dst, cudaStream_t st,
                       bool *done);

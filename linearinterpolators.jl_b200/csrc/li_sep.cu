@@ -318,6 +318,17 @@ static int sep_apply_host_impl(int adjoint, int ndim, const li_table *const *tab
     if (rc == LI_OK) rc = li::staging(1, nout ? nout : 1, &ddst, stream);
     if (rc == LI_OK && wsb) rc = li::staging(2, wsb, &ws, stream);
     if (rc != LI_OK) return rc;
+    // large fused 2-D applies: uploads, kernels and downloads pipelined over bands of rows
+    if (ndim == 2 && tabs[0] && tabs[1] && nbatch == 1 && beta == 0.0 && alpha != 0.0 && variant != LI_VARIANT_ATOMIC &&
+        nin + nout >= (size_t)(32u << 20)) {
+        bool banded = false;
+        rc = li::sep2d_host_banded(adjoint, tabs[0], tabs[1], alpha, src_host, dst_host, dsrc, ddst, st, &banded);
+        if (rc != LI_OK) return rc;
+        if (banded) {
+            if (sync) LI_CUDA(cudaStreamSynchronize(st));
+            return LI_OK;
+        }
+    }
     cudaError_t e = cudaMemcpyAsync(dsrc, src_host, nin, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && beta != 0.0) e = cudaMemcpyAsync(ddst, dst_host, nout, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {

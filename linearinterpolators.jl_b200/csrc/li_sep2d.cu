@@ -16,6 +16,7 @@
 //             dim-1 gather) are the fallback for unaligned sources and for down-sampling along dim 1.
 //   No kernel uses atomics; every dst element is written once by its owner, in a fixed order (deterministic).
 #include <algorithm>
+#include <map>
 
 #include "li_common.cuh"
 #include "li_sep2d.cuh"
@@ -68,7 +69,7 @@ sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, c
     int bid = blockIdx.x;
     const int strip = bid % a.tiles1;
     bid /= a.tiles1;
-    const int chunk = bid % a.tiles2;
+    const int chunk = bid % a.tiles2 + a.chunk0;
     const int64_t batch = bid / a.tiles2;
     const int i1_0 = strip * TO1;
     const int i2a = chunk * CR, rows = min(CR, a.n2 - i2a);   // output rows [i2a, i2a + rows)
@@ -631,6 +632,12 @@ sep2d_adj_regular_kernel(const SepArgs<T> a, const int TD1)
 
 
 // ---------------------------------------------------------------------------------------------
+BandCtl *&sep2d_band()
+{
+    static thread_local BandCtl *ctl = nullptr;
+    return ctl;
+}
+
 int sep2d_num_sms()
 {
     static thread_local int n = 0;
@@ -667,6 +674,24 @@ static int launch_fwd(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     const size_t smem = ((size_t)FWD_NSTAGE * K * a.F1MAX + (size_t)CR * S2) * sizeof(T) +
                         (size_t)((NCNT + 1) & ~1) * sizeof(int) + FWD_NSTAGE * sizeof(uint64_t);
     if (smem > (size_t)kSmemLimit) return LI_OK;   // footprint too large for staging: decline
+    if (BandCtl *bc = sep2d_band()) {   // host-buffer pipeline: describe the chunks, or launch a band of them
+        if (bc->mode == 1) {
+            const std::vector<int32_t> *bh = nullptr;
+            rc = table_base_host(t2, st, &bh);
+            if (rc != LI_OK) return rc;
+            bc->row_begin.assign(a.tiles2 + 1, a.n2);
+            bc->src_end.assign(a.tiles2, 0);
+            for (int k = 0; k < a.tiles2; ++k) {
+                bc->row_begin[k] = k * CR;
+                const int last = std::min((k + 1) * CR, a.n2) - 1;
+                bc->src_end[k] = std::min(std::max((*bh)[last] + S2 - 1, 0), a.m2 - 1) + 1;
+            }
+            *done = true;
+            return LI_OK;
+        }
+        a.chunk0 = bc->chunk0;
+        a.tiles2 = bc->nchunks;
+    }
     const int64_t blocks = (int64_t)a.tiles1 * a.tiles2 * nbatch;
     LI_REQUIRE(blocks <= 0x7fffffffLL, LI_ERR_UNSUPPORTED, "too many tiles");
     const bool pair = t1->max_step <= 1, beta = a.beta != (T)0;
@@ -696,6 +721,7 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
         int rcs = sep2d_adj_stream<T>(a, t1, t2, nbatch, st, done);
         if (rcs != LI_OK || *done) return rcs;
     }
+    if (sep2d_band()) return LI_OK;   // (the tile kernels have no banded form: the host pipeline falls back)
     int rc = table_ensure_rowstart(t1, st);
     if (rc == LI_OK) rc = table_ensure_fold(t2, st);
     if (rc != LI_OK) return rc;
@@ -830,6 +856,81 @@ int sep2d_fused_apply(int adjoint, const li_table *t1, const li_table *t2, int64
     if (getenv("LI_B200_NO_FUSED")) return LI_OK;
     return t1->dtype == LI_F32 ? fused_T<float>(adjoint, t1, t2, nbatch, alpha, src, beta, dst, st, done)
                                : fused_T<double>(adjoint, t1, t2, nbatch, alpha, src, beta, dst, st, done);
+}
+
+
+// Host-buffer pipeline of one fused 2-D apply (beta = 0, one image): the chunks of the launch are grouped into bands
+// along dim 2; the src rows a band needs go up on a private copy stream while earlier bands compute, and every band's
+// dst rows go down as soon as its kernel has run, so uploads, kernels and downloads of one apply overlap (and two
+// applies on two caller streams keep both copy engines busy).  dsrc / ddst are full-size device staging buffers.
+// *done stays false when the problem has no banded form (the caller then does upload - apply - download).
+int sep2d_host_banded(int adjoint, const li_table *t1, const li_table *t2, double alpha, const void *src_host, void *dst_host,
+                      void *dsrc, void *ddst, cudaStream_t st, bool *done)
+{
+    *done = false;
+    constexpr int NBMAX = 8;
+    static const bool off = getenv("LI_B200_NO_BANDS") != nullptr;
+    if (off || !sep2d_fused_supported(t1, t2)) return LI_OK;
+    struct Guard {
+        ~Guard() { sep2d_band() = nullptr; }
+    } guard;
+    BandCtl bc;
+    bc.mode = 1;
+    sep2d_band() = &bc;
+    bool planned = false;
+    int rc = sep2d_fused_apply(adjoint, t1, t2, 1, alpha, dsrc, 0.0, ddst, st, &planned);
+    if (rc != LI_OK || !planned) return rc;
+    const int nchunks = (int)bc.src_end.size();
+    const int NB = std::min(NBMAX, nchunks);
+    if (NB < 2 || (int)bc.row_begin.size() != nchunks + 1) return LI_OK;
+    const size_t es = t1->dtype == LI_F32 ? 4 : 8;
+    const int64_t src_rows = adjoint ? t2->nrows : t2->ncols, src_w = adjoint ? t1->nrows : t1->ncols;
+    const int64_t dst_w = adjoint ? t1->ncols : t1->nrows;
+    const size_t src_rb = (size_t)src_w * es, dst_rb = (size_t)dst_w * es;
+
+    struct Aux {
+        cudaStream_t sh = nullptr;
+        cudaEvent_t start = nullptr, ev[NBMAX] = {};
+    };
+    static thread_local std::map<cudaStream_t, Aux> auxmap;
+    Aux &ax = auxmap[st];
+    if (!ax.sh) {
+        LI_CUDA(cudaStreamCreateWithFlags(&ax.sh, cudaStreamNonBlocking));
+        LI_CUDA(cudaEventCreateWithFlags(&ax.start, cudaEventDisableTiming));
+        for (int b = 0; b < NBMAX; ++b) LI_CUDA(cudaEventCreateWithFlags(&ax.ev[b], cudaEventDisableTiming));
+    }
+    // uploads: after everything already queued on the caller's stream (the staging buffers may still be in use)
+    LI_CUDA(cudaEventRecord(ax.start, st));
+    LI_CUDA(cudaStreamWaitEvent(ax.sh, ax.start, 0));
+    int64_t copied = 0;
+    for (int b = 0; b < NB; ++b) {
+        const int c1 = (int)((int64_t)nchunks * (b + 1) / NB);
+        const int64_t need = std::min<int64_t>(std::max<int64_t>(bc.src_end[c1 - 1], copied), src_rows);
+        if (need > copied)
+            LI_CUDA(cudaMemcpyAsync((char *)dsrc + copied * src_rb, (const char *)src_host + copied * src_rb,
+                                    (size_t)(need - copied) * src_rb, cudaMemcpyHostToDevice, ax.sh));
+        copied = need;
+        LI_CUDA(cudaEventRecord(ax.ev[b], ax.sh));
+    }
+    // bands: kernel, then download, in order on the caller's stream
+    for (int b = 0; b < NB; ++b) {
+        const int c0 = (int)((int64_t)nchunks * b / NB), c1 = (int)((int64_t)nchunks * (b + 1) / NB);
+        LI_CUDA(cudaStreamWaitEvent(st, ax.ev[b], 0));
+        bc.mode = 2, bc.chunk0 = c0, bc.nchunks = c1 - c0;
+        bool ok = false;
+        rc = sep2d_fused_apply(adjoint, t1, t2, 1, alpha, dsrc, 0.0, ddst, st, &ok);
+        if (rc == LI_OK && !ok) {
+            set_error("internal: the fused kernel declined a band it had planned");
+            rc = LI_ERR_UNSUPPORTED;
+        }
+        if (rc != LI_OK) return rc;
+        const int64_t r0 = bc.row_begin[c0], r1 = bc.row_begin[c1];
+        if (r1 > r0)
+            LI_CUDA(cudaMemcpyAsync((char *)dst_host + r0 * dst_rb, (const char *)ddst + r0 * dst_rb, (size_t)(r1 - r0) * dst_rb,
+                                    cudaMemcpyDeviceToHost, st));
+    }
+    *done = true;
+    return LI_OK;
 }
 
 }  // namespace li

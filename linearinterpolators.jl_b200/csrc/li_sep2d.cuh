@@ -1,6 +1,7 @@
 // li_sep2d.cuh -- types and device helpers shared by the fused 2-D separable kernels (li_sep2d.cu, li_sep2d_adjs.cu).
 #pragma once
 #include <algorithm>
+#include <vector>
 
 #include "li_common.cuh"
 
@@ -68,6 +69,7 @@ struct SepArgs {
     int n1, n2;                    // "rows" side (fine grid for an upsampling operator)
     int m1, m2;                    // "columns" side
     int tiles1, tiles2;
+    int chunk0;                    // first chunk (along dim 2) of this launch: bands of the host-buffer pipeline
     int F1MAX, F2MAX;              // forward: footprint bounds; adjoint: F2MAX = max src rows feeding one row group
     int vec_ok;                    // rows of the big array are 2-element-vector aligned
     T alpha, beta;
@@ -135,6 +137,17 @@ static int set_smem(KernT kern, size_t smem)
     if (smem > 48 * 1024) LI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return LI_OK;
 }
+
+// Banding of the fused kernels along dim 2 for the host-buffer entry points (sep2d_host_banded): the launchers consult
+// this thread-local control block.  mode 1 = describe the chunks of the launch without launching (plan), mode 2 =
+// launch only chunks [chunk0, chunk0 + nchunks).
+struct BandCtl {
+    int mode = 0;
+    int chunk0 = 0, nchunks = 0;
+    // filled by the plan: chunk k produces dst rows [row_begin[k], row_begin[k+1]) and reads src rows < src_end[k]
+    std::vector<int> row_begin, src_end;
+};
+BandCtl *&sep2d_band();
 
 // streaming adjoint (li_sep2d_adjs.cu): *done stays false when the kernel declines the problem
 template <typename T>

@@ -79,7 +79,7 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
     int bid = blockIdx.x;
     const int strip = bid % a.tiles1;
     bid /= a.tiles1;
-    const int chunk = bid % a.tiles2;
+    const int chunk = bid % a.tiles2 + a.chunk0;
     const int64_t batch = bid / a.tiles2;
     const int c0 = strip * NT, c1 = min(c0 + NT, a.m1);      // owned dst columns
     const int va = a.cstart[chunk], vb = a.cstart[chunk + 1];   // owned dst rows (chunks of about equal cost, <= CR rows)
@@ -410,7 +410,8 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     int CR = 0, nrmax = 0;
     // chunks that must run the generic loop (array edges, irregular rates) are charged 30 % of a chunk, i.e. made
     // shorter: all CTAs of the single wave then finish together
-    rc = table_chunk_plan(t2, nchunks, 0.3, st, &a.cstart, &CR, &nrmax);
+    const li_table::ChunkPlan *plan = nullptr;
+    rc = table_chunk_plan(t2, nchunks, 0.3, st, &a.cstart, &CR, &nrmax, &plan);
     if (rc != LI_OK) return rc;
     if (CR > 4096) return LI_OK;
     const int NRMAX = (std::max(nrmax, 1) + 1) & ~1;
@@ -421,6 +422,16 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
         fprintf(stderr, "[li_b200] adj stream: NU %d P1 %d CR %d NRMAX %d smem %zu tiles %d x %d R %d\n", NU, P1, CR, NRMAX,
                 smem, a.tiles1, a.tiles2, R);
     if (smem > (size_t)kSmemLimit) return LI_OK;
+    if (BandCtl *bc = sep2d_band()) {   // host-buffer pipeline: describe the chunks, or launch a band of them
+        if (bc->mode == 1) {
+            bc->row_begin.assign(plan->starts_host.begin(), plan->starts_host.end());
+            bc->src_end.assign(plan->src_end_host.begin(), plan->src_end_host.end());
+            *done = true;
+            return LI_OK;
+        }
+        a.chunk0 = bc->chunk0;
+        a.tiles2 = bc->nchunks;
+    }
     const int64_t blocks = (int64_t)a.tiles1 * a.tiles2 * nbatch;
     LI_REQUIRE(blocks <= 0x7fffffffLL, LI_ERR_UNSUPPORTED, "too many tiles");
     a.bp1 = t1->rowstart, a.bfold1 = t1->bfold, a.W1f = (const T *)t1->Wfold;

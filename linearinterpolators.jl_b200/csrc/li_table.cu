@@ -614,8 +614,20 @@ int table_tile_rows(const li_table *t, int TD2, cudaStream_t st, const int32_t *
     return LI_OK;
 }
 
+int table_base_host(const li_table *t, cudaStream_t st, const std::vector<int32_t> **base)
+{
+    std::lock_guard<std::mutex> lock(t->mu);
+    if (t->base_host.empty()) {
+        t->base_host.resize(t->nrows);
+        LI_CUDA(cudaMemcpyAsync(t->base_host.data(), t->base, t->nrows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        LI_CUDA(cudaStreamSynchronize(st));
+    }
+    *base = &t->base_host;
+    return LI_OK;
+}
+
 int table_chunk_plan(const li_table *t, int nchunks, double penalty, cudaStream_t st, const int32_t **starts, int *crmax,
-                     int *nrmax)
+                     int *nrmax, const li_table::ChunkPlan **plan_out)
 {
     int rc = table_ensure_fold(t, st);
     if (rc != LI_OK) return rc;
@@ -648,10 +660,13 @@ int table_chunk_plan(const li_table *t, int nchunks, double penalty, cudaStream_
         }
         b[nchunks] = m;
         li_table::ChunkPlan plan;
+        plan.starts_host = b;
+        plan.src_end_host.assign(nchunks, 0);
         for (int k = 0; k < nchunks; ++k) {
             const int va = b[k], vb = b[k + 1];
             plan.crmax = std::max(plan.crmax, vb - va);
             if (vb > va) plan.nrmax = std::max(plan.nrmax, (int)(bpf[vb - 1 + S] - bpf[va]));
+            plan.src_end_host[k] = vb > va ? bpf[vb - 1 + S] : (k ? plan.src_end_host[k - 1] : 0);
         }
         LI_CUDA(cudaMalloc(&plan.starts, (nchunks + 1) * sizeof(int32_t)));
         cudaError_t e = cudaMemcpyAsync(plan.starts, b.data(), (nchunks + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st);
@@ -666,6 +681,7 @@ int table_chunk_plan(const li_table *t, int nchunks, double penalty, cudaStream_
     *starts = it->second.starts;
     *crmax = it->second.crmax;
     *nrmax = it->second.nrmax;
+    if (plan_out) *plan_out = &it->second;
     return LI_OK;
 }
 
