@@ -113,6 +113,7 @@ int table_tile_rows(const li_table *t, int TD2, cudaStream_t st, const int32_t *
 int table_chunk_plan(const li_table *t, int nchunks, double penalty, cudaStream_t st, const int32_t **starts, int *crmax,
                      int *nrmax, const li_table::ChunkPlan **plan = nullptr);
 int table_base_host(const li_table *t, cudaStream_t st, const std::vector<int32_t> **base);
+int table_identity(int dtype, int64_t n, cudaStream_t st, const li_table **out);   // cached S = 1 identity operator
 // builds a table from device positions into preallocated device arrays (used by the OTF operators)
 int table_create_impl(const li_kernel_desc *ker, const void *pos_dev, int64_t nrows, int64_t ncols,
                       cudaStream_t st, li_table **out);

@@ -838,6 +838,7 @@ static int fused_T(int adjoint, const li_table *t1, const li_table *t2, int64_t 
         return adjoint ? launch_adj<T, A1, A2>(a, t1, t2, nbatch, st, done)             \
                        : launch_fwd<T, A1, A2>(a, t1, t2, nbatch, st, done);
     LI_SEP(2, 2) LI_SEP(4, 4) LI_SEP(6, 6) LI_SEP(2, 4) LI_SEP(4, 2) LI_SEP(4, 6) LI_SEP(6, 4) LI_SEP(3, 3)
+    LI_SEP(2, 1) LI_SEP(3, 1) LI_SEP(4, 1) LI_SEP(6, 1)   // (second factor = identity: 1-D applies along dim 1)
 #undef LI_SEP
     return LI_OK;   // size pair not built: decline
 }

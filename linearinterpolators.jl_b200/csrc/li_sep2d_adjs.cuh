@@ -458,6 +458,7 @@ int sep2d_adj_stream(SepArgs<T> &a, const li_table *t1, const li_table *t2, int6
     LI_SEP(4, 4)
 #else
     LI_SEP(2, 2) LI_SEP(4, 4) LI_SEP(6, 6) LI_SEP(2, 4) LI_SEP(4, 2) LI_SEP(4, 6) LI_SEP(6, 4) LI_SEP(3, 3)
+    LI_SEP(2, 1) LI_SEP(3, 1) LI_SEP(4, 1) LI_SEP(6, 1)
 #endif
 #undef LI_SEP
     return LI_OK;

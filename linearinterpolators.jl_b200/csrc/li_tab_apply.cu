@@ -518,6 +518,31 @@ int tab_apply_impl(int adjoint, const li_table *t, int64_t npre, int64_t npost, 
     if (alpha == 0.0) return vscale_impl(t->dtype, dst, nout, beta, st);  // src/tabulated.jl:352-353
     LI_REQUIRE(src, LI_ERR_ARG, "null source");
     LI_REQUIRE(npre * npost * std::max(t->ncols, t->nrows) < (1LL << 62), LI_ERR_DIM, "array too large");
+    // Contiguous dimension of a sorted table over many columns: the fused 2-D kernels with the identity as second
+    // factor (staged rows, TMA ring) instead of the gather kernels below.  [len, npost] is viewed as
+    // [len, n2, nbatch] with n2 a divisor of npost, so the identity table stays small.
+    if (npre == 1 && npost >= 64 && t->windowed && t->monotone && variant != LI_VARIANT_ATOMIC &&
+        (t->S == 2 || t->S == 3 || t->S == 4 || t->S == 6) && !getenv("LI_B200_NO_STREAM_DN")) {
+        int64_t n2 = 0;
+        if (npost <= 4096) {
+            n2 = npost;
+        } else {
+            for (int64_t c = 4096; c >= 256; --c)
+                if (npost % c == 0) {
+                    n2 = c;
+                    break;
+                }
+            if (!n2 && npost <= (1LL << 22)) n2 = npost;
+        }
+        if (n2) {
+            const li_table *ident = nullptr;
+            int rc = table_identity(t->dtype, n2, st, &ident);
+            if (rc != LI_OK) return rc;
+            bool done = false;
+            rc = sep2d_fused_apply(adjoint, t, ident, npost / n2, alpha, src, beta, dst, st, &done);
+            if (rc != LI_OK || done) return rc;
+        }
+    }
     if (!adjoint)
         return t->dtype == LI_F32 ? direct_T<float>(t, npre, npost, alpha, beta, src, dst, st)
                                   : direct_T<double>(t, npre, npost, alpha, beta, src, dst, st);

@@ -6,6 +6,8 @@
 
 #include <climits>
 #include <functional>
+#include <map>
+#include <tuple>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -611,6 +613,53 @@ int table_tile_rows(const li_table *t, int TD2, cudaStream_t st, const int32_t *
     }
     *list = it->second.first;
     *nregular = it->second.second;
+    return LI_OK;
+}
+
+// Identity operator as a table (S = 1, row i reads column i with weight 1): the second factor that lets a 1-D apply
+// along the contiguous dimension run through the fused 2-D kernels.  Cached per (device, dtype, n), never freed.
+template <typename T>
+__global__ void identity_table_kernel(int32_t *__restrict__ J, T *__restrict__ W, int32_t *__restrict__ base, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        J[i] = i;
+        base[i] = i;
+        W[i] = (T)1;
+    }
+}
+
+int table_identity(int dtype, int64_t n, cudaStream_t st, const li_table **out)
+{
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int64_t>, li_table *> cache;
+    int dev = 0;
+    LI_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_tuple(dev, dtype, n);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        li_table *t = nullptr;
+        int rc = alloc_table(dtype, 1, n, n, &t);
+        if (rc != LI_OK) return rc;
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        if (dtype == LI_F32)
+            identity_table_kernel<float><<<blocks, 256, 0, st>>>(t->J, (float *)t->W, t->base, (int)n);
+        else
+            identity_table_kernel<double><<<blocks, 256, 0, st>>>(t->J, (double *)t->W, t->base, (int)n);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_error("identity table failed: %s", cudaGetErrorString(e));
+            li_table_destroy(t);
+            return LI_ERR_CUDA;
+        }
+        t->windowed = t->monotone = true;
+        t->max_step = 1;
+        it = cache.emplace(key, t).first;
+    }
+    *out = it->second;
     return LI_OK;
 }
 

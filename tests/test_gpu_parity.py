@@ -260,6 +260,32 @@ def test_two_factors_on_3d_array_use_fused_kernels(li):
     assert_close(li.to_host((A1 * A2).adj * out), refa, T, factor=64)
 
 
+@pytest.mark.parametrize("T", DTYPES)
+@pytest.mark.parametrize("npost", [64, 5000, 4099])   # one identity table; a divisor of npost as second dimension; prime
+def test_tab_apply_contiguous_dim_through_fused_kernels(li, T, npost):
+    """1-D applies along the first dimension of a sorted table over many columns run through the fused 2-D kernels
+    with the identity as second factor."""
+    rng = np.random.default_rng(29)
+    ncols = 96
+    for entry, cond in ((KERNELS[1], O.FLAT), (KERNELS[2], O.SAFEFLAT), (KERNELS[8], O.FLAT), (KERNELS[9], O.SAFEFLAT)):
+        for nrows, xs in ((192, np.linspace(1, ncols, 192)), (100, np.linspace(-5.5, ncols + 8.25, 100))):
+            J, W = O.maketable(oracle_kernel(entry, cond), xs.astype(T), ncols, T)
+            A = li.TabulatedInterpolator(T, 1, product_kernel(li, entry, cond, T), xs, ncols)
+            src = np.asfortranarray(rng.standard_normal((ncols, npost)).astype(T))
+            y = np.asfortranarray(rng.standard_normal((nrows, npost)).astype(T))
+            for alpha, beta in ((1, 0), (0.5, -2)):
+                d0 = np.asfortranarray(rng.standard_normal((nrows, npost)).astype(T))
+                ref = O.tab_direct(J, W, ncols, 1, src, alpha, beta, d0.copy(order="F"))
+                dd = li.to_device(d0)
+                li.apply_b(alpha, li.Direct, A, li.to_device(src), False, beta, dd)
+                assert_close(li.to_host(dd), ref, T, factor=4)
+                c0 = np.asfortranarray(rng.standard_normal((ncols, npost)).astype(T))
+                refa = O.tab_adjoint(J, W, ncols, 1, y, alpha, beta, c0.copy(order="F"))
+                dc = li.to_device(c0)
+                li.apply_b(alpha, li.Adjoint, A, li.to_device(y), False, beta, dc)
+                assert_close(li.to_host(dc), refa, T, scale=float(np.max(np.abs(refa))) + 1, factor=16)
+
+
 def test_beta_zero_never_reads_dst(li):
     T = np.float32
     A = li.TabulatedInterpolator(T, li.CatmullRomSpline(T), np.linspace(1, 9, 33), 9)
