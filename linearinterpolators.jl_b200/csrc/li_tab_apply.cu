@@ -521,7 +521,9 @@ int tab_apply_impl(int adjoint, const li_table *t, int64_t npre, int64_t npost, 
     // Contiguous dimension of a sorted table over many columns: the fused 2-D kernels with the identity as second
     // factor (staged rows, TMA ring) instead of the gather kernels below.  [len, npost] is viewed as
     // [len, n2, nbatch] with n2 a divisor of npost, so the identity table stays small.
-    if (npre == 1 && npost >= 64 && t->windowed && t->monotone && variant != LI_VARIANT_ATOMIC &&
+    // (short vectors leave most of a 256-thread strip idle: measured break-even at a length of about 96)
+    if (npre == 1 && npost >= 64 && std::max(t->nrows, t->ncols) >= 96 && t->windowed && t->monotone &&
+        variant != LI_VARIANT_ATOMIC &&
         (t->S == 2 || t->S == 3 || t->S == 4 || t->S == 6) && !getenv("LI_B200_NO_STREAM_DN")) {
         int64_t n2 = 0;
         if (npost <= 4096) {
