@@ -158,8 +158,10 @@ __device__ __forceinline__ VecN<T, V> ldv(const T *p)
     VecN<T, V> r;
     if constexpr (sizeof(T) * V == 16)
         *reinterpret_cast<uint4 *>(r.v) = *reinterpret_cast<const uint4 *>(p);
-    else
+    else if constexpr (sizeof(T) * V == 8)
         *reinterpret_cast<uint2 *>(r.v) = *reinterpret_cast<const uint2 *>(p);
+    else
+        r.v[0] = p[0];
     return r;
 }
 template <typename T, int V>
@@ -167,8 +169,10 @@ __device__ __forceinline__ void stv(T *p, const VecN<T, V> &r)
 {
     if constexpr (sizeof(T) * V == 16)
         *reinterpret_cast<uint4 *>(p) = *reinterpret_cast<const uint4 *>(r.v);
-    else
+    else if constexpr (sizeof(T) * V == 8)
         *reinterpret_cast<uint2 *>(p) = *reinterpret_cast<const uint2 *>(r.v);
+    else
+        p[0] = r.v[0];
 }
 __device__ __forceinline__ int clampi_(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
 
@@ -347,14 +351,16 @@ tab_adjoint_atomic_kernel(const int32_t *__restrict__ J, const T *__restrict__ W
     }
 }
 
-// the streaming kernels need a windowed monotone table with a compile-time S and 16-byte aligned vectors of V elements
+// the streaming kernels need a windowed monotone table with a compile-time S; returns the widest vector (elements per
+// thread, 16 bytes at most) that the length of the contiguous index and the alignment of the arrays allow, 0 = none
 template <typename T, int SC>
-static bool stream_ok(const li_table *t, int64_t npre, const void *src, const void *dst)
+static int stream_vec(const li_table *t, int64_t npre, const void *src, const void *dst)
 {
-    constexpr int V = 16 / (int)sizeof(T);
     static const bool off = getenv("LI_B200_NO_STREAM_DN") != nullptr;
-    return SC > 0 && !off && t->windowed && t->monotone && npre % V == 0 && ((uintptr_t)src) % 16 == 0 &&
-           ((uintptr_t)dst) % 16 == 0;
+    if (SC == 0 || off || !t->windowed || !t->monotone) return 0;
+    for (int V = 16 / (int)sizeof(T); V > 1; V >>= 1)
+        if (npre % V == 0 && ((uintptr_t)src) % (V * sizeof(T)) == 0 && ((uintptr_t)dst) % (V * sizeof(T)) == 0) return V;
+    return 1;
 }
 
 // chunks along the interpolated dimension: enough CTAs to fill the machine (about 8 per SM with the other two grid
@@ -378,16 +384,24 @@ static int launch_direct(const li_table *t, int64_t npre, int64_t npost, T alpha
         dim3 grid((nrows + 255) / 256, (unsigned)std::min<int64_t>(npost, 65535));
         tab_direct_d1_kernel<T, SC><<<grid, 256, 0, st>>>(t->J, (const T *)t->W, t->S, nrows, ncols, npost, alpha,
                                                          beta, src, dst);
-    } else if (stream_ok<T, SC>(t, npre, src, dst)) {
-        constexpr int V = 16 / (int)sizeof(T);
+    } else if (const int V = stream_vec<T, SC>(t, npre, src, dst)) {
         const int64_t npv = npre / V;
         const int threads = npv >= 256 ? 256 : (npv >= 128 ? 128 : (npv >= 64 ? 64 : 32));
         const unsigned gx = (unsigned)((npv + threads - 1) / threads);
         int CR, chunks;
         stream_chunks(nrows, (int64_t)gx * std::min<int64_t>(npost, 65535), SC, &CR, &chunks);
         dim3 grid(gx, chunks, (unsigned)std::min<int64_t>(npost, 65535));
-        tab_direct_stream_kernel<T, (SC ? SC : 1), V><<<grid, threads, 0, st>>>(t->base, (const T *)t->W, nrows, ncols, npv,
-                                                                              npost, CR, alpha, beta, src, dst);
+        constexpr int S_ = SC ? SC : 1, VMAX = 16 / (int)sizeof(T);
+#define LI_DSTREAM(VV)                                                                                                  \
+    tab_direct_stream_kernel<T, S_, VV><<<grid, threads, 0, st>>>(t->base, (const T *)t->W, nrows, ncols, npv, npost, CR, \
+                                                                 alpha, beta, src, dst)
+        if (V == VMAX)
+            LI_DSTREAM(VMAX);
+        else if (V == 2)
+            LI_DSTREAM(2);
+        else
+            LI_DSTREAM(1);
+#undef LI_DSTREAM
     } else {
         constexpr int RB = 4;
         const int threads = npre >= 256 ? 256 : (npre >= 128 ? 128 : (npre >= 64 ? 64 : 32));
@@ -421,10 +435,11 @@ static int launch_adjoint_stream(const li_table *t, int64_t npre, int64_t npost,
                                  cudaStream_t st, bool *done)
 {
     *done = false;
-    if (!stream_ok<T, S>(t, npre, src, dst)) return LI_OK;
+    const int V = stream_vec<T, S>(t, npre, src, dst);
+    if (!V) return LI_OK;
     int rc = table_ensure_fold(t, st);
     if (rc != LI_OK) return rc;
-    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int VMAX = 16 / (int)sizeof(T);
     const int nrows = (int)t->nrows, ncols = (int)t->ncols;
     const int64_t npv = npre / V;
     const int threads = npv >= 256 ? 256 : (npv >= 128 ? 128 : (npv >= 64 ? 64 : 32));
@@ -432,8 +447,16 @@ static int launch_adjoint_stream(const li_table *t, int64_t npre, int64_t npost,
     int CR, chunks;
     stream_chunks(ncols, (int64_t)gx * std::min<int64_t>(npost, 65535), S, &CR, &chunks);
     dim3 grid(gx, chunks, (unsigned)std::min<int64_t>(npost, 65535));
-    tab_adjoint_stream_kernel<T, S, V><<<grid, threads, 0, st>>>(t->base, t->bpf, (const T *)t->Wfold, nrows, ncols, npv, npost,
-                                                               CR, alpha, beta, src, dst);
+#define LI_ASTREAM(VV)                                                                                                   \
+    tab_adjoint_stream_kernel<T, S, VV><<<grid, threads, 0, st>>>(t->base, t->bpf, (const T *)t->Wfold, nrows, ncols, npv, \
+                                                                 npost, CR, alpha, beta, src, dst)
+    if (V == VMAX)
+        LI_ASTREAM(VMAX);
+    else if (V == 2)
+        LI_ASTREAM(2);
+    else
+        LI_ASTREAM(1);
+#undef LI_ASTREAM
     LI_CHECK_LAUNCH();
     *done = true;
     return LI_OK;
