@@ -53,7 +53,7 @@ struct FwdK {   // source rows per stage: a multiple of S2 (static window rotati
 };
 
 template <typename T, int S1, int S2, bool PAIR, bool BETA>
-__global__ void __launch_bounds__(FWD_NT, (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : 2)
+__global__ void __launch_bounds__(FWD_NT, (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : (sizeof(T) == 4 ? 3 : 2))
 sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, const int NCNT /* staged-row counters */)
 {
     constexpr int NT = FWD_NT, TO1 = 2 * NT, K = FwdK<S2>::value, NSTAGE = FWD_NSTAGE;
