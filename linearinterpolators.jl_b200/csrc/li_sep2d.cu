@@ -657,7 +657,7 @@ static int launch_fwd(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     a.tiles1 = (a.n1 + TO1 - 1) / TO1;
     // chunks of output rows: about one wave of 4 CTAs per SM, chunk length a multiple of 8 and at most FWD_MAXCR
     const int64_t target = (int64_t)sep2d_num_sms() * 4 * FWD_WAVES_;
-    int chunks = (int)std::max<int64_t>(1, (target + a.tiles1 * nbatch - 1) / (a.tiles1 * nbatch));
+    int chunks = (int)std::max<int64_t>(1, target / (a.tiles1 * nbatch));   // (rounded down: whole waves)
     int CR = (a.n2 + chunks - 1) / chunks;
     CR = std::min(FWD_MAXCR, std::max(8, (CR + 7) & ~7));
     a.tiles2 = (a.n2 + CR - 1) / CR;

@@ -403,7 +403,9 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     // chunks of dst rows: about ADS_PER_SM CTAs per SM (a thread walks its rows one after the other, so a small problem
     // cut into few long chunks is latency-bound), but at least 4*S2 rows per chunk (each chunk re-reads S2-1 halo rows)
     const int64_t target = (int64_t)sep2d_num_sms() * ADS_PER_SM * ADS_WAVES_;
-    const int chunks = (int)std::max<int64_t>(1, (target + a.tiles1 * nbatch - 1) / (a.tiles1 * nbatch));
+    // (rounded DOWN: a grid slightly larger than the resident slots would put its last CTAs into a second round and
+    // nearly double the kernel time -- measured on 8192^2 at rate 1: 608 CTAs on 592 slots)
+    const int chunks = (int)std::max<int64_t>(1, target / (a.tiles1 * nbatch));
     // (at least 4*S2 rows per chunk: each chunk re-reads S2-1 halo rows)
     const int nchunks = std::max(1, std::min(chunks, a.m2 / std::max(8, 4 * S2)));
     a.tiles2 = nchunks;
