@@ -377,6 +377,25 @@ static int launch_stream(SepArgs<T> &a, int CR, int NRMAX, size_t smem, int64_t 
     return LI_OK;
 }
 
+// resident CTAs per SM of one kernel instance with `smem` bytes of dynamic shared memory (registers decide for the
+// wide instances); cached per instance
+template <typename T, int S1, int S2, int NU, int R>
+static int stream_occupancy(size_t smem)
+{
+    static thread_local int cached = 0;
+    static thread_local size_t cached_smem = 0;
+    if (cached && cached_smem == smem) return cached;
+    auto kern = sep2d_adj_stream_kernel<T, S1, S2, NU, R>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ADS_NT, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 1;
+    }
+    cached = occ, cached_smem = smem;
+    return occ;
+}
+
 template <typename T, int S1, int S2>
 static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64_t nbatch, cudaStream_t st, bool *done)
 {
@@ -402,7 +421,20 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     a.tiles1 = (a.m1 + ADS_NT - 1) / ADS_NT;
     // chunks of dst rows: about ADS_PER_SM CTAs per SM (a thread walks its rows one after the other, so a small problem
     // cut into few long chunks is latency-bound), but at least 4*S2 rows per chunk (each chunk re-reads S2-1 halo rows)
-    const int64_t target = (int64_t)sep2d_num_sms() * ADS_PER_SM * ADS_WAVES_;
+    // (the grid is sized for the CTAs that are really resident: the wide instances hold 2 or 3 per SM, not 4)
+    const int R = (t2->irrp && (t2->reg_R == 1 || t2->reg_R == 2)) ? t2->reg_R : 0;
+    int occ = ADS_PER_SM;
+    {
+        const size_t smem_est = ((size_t)ADS_NSTAGE * K * P1) * sizeof(T) + 8 * 1024;
+#define LI_OCC(NUU, RR) \
+    if (NU == NUU && R == RR) occ = stream_occupancy<T, S1, S2, NUU, RR>(smem_est);
+        LI_OCC(NU_S, 0) LI_OCC(NU_S, 1) LI_OCC(NU_S, 2) LI_OCC(NU_L, 0) LI_OCC(NU_L, 1) LI_OCC(NU_L, 2)
+#undef LI_OCC
+    }
+    occ = std::min(occ, ADS_PER_SM);
+    // (a kernel that holds fewer CTAs per SM gets as many rounds as needed to keep the chunks short)
+    const int rounds = std::max(1, ADS_PER_SM / occ);
+    const int64_t target = (int64_t)sep2d_num_sms() * occ * rounds * ADS_WAVES_;
     // (rounded DOWN: a grid slightly larger than the resident slots would put its last CTAs into a second round and
     // nearly double the kernel time -- measured on 8192^2 at rate 1: 608 CTAs on 592 slots)
     const int chunks = (int)std::max<int64_t>(1, target / (a.tiles1 * nbatch));
@@ -419,10 +451,9 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     const int NRMAX = (std::max(nrmax, 1) + 1) & ~1;
     const size_t smem = ((size_t)ADS_NSTAGE * K * P1 + (size_t)NRMAX * S2) * sizeof(T) +
                         (size_t)((CR + 2 * S2 + 1) & ~1) * sizeof(int) + ADS_NSTAGE * sizeof(uint64_t);
-    const int R = (t2->irrp && (t2->reg_R == 1 || t2->reg_R == 2)) ? t2->reg_R : 0;
     if (trace)
-        fprintf(stderr, "[li_b200] adj stream: NU %d P1 %d CR %d NRMAX %d smem %zu tiles %d x %d R %d\n", NU, P1, CR, NRMAX,
-                smem, a.tiles1, a.tiles2, R);
+        fprintf(stderr, "[li_b200] adj stream: NU %d P1 %d CR %d NRMAX %d smem %zu tiles %d x %d R %d occ %d\n", NU, P1, CR,
+                NRMAX, smem, a.tiles1, a.tiles2, R, occ);
     if (smem > (size_t)kSmemLimit) return LI_OK;
     if (BandCtl *bc = sep2d_band()) {   // host-buffer pipeline: describe the chunks, or launch a band of them
         if (bc->mode == 1) {
