@@ -655,8 +655,10 @@ static int launch_fwd(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
 {
     constexpr int TO1 = 2 * FWD_NT, K = FwdK<S2>::value;
     a.tiles1 = (a.n1 + TO1 - 1) / TO1;
-    // chunks of output rows: about one wave of 4 CTAs per SM, chunk length a multiple of 8 and at most FWD_MAXCR
-    const int64_t target = (int64_t)sep2d_num_sms() * 4 * FWD_WAVES_;
+    // chunks of output rows: FWD_WAVES_ whole waves of the CTAs resident per SM (the kernel's launch bound), chunk
+    // length a multiple of 8 and at most FWD_MAXCR
+    constexpr int PER_SM = (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : (sizeof(T) == 4 ? 3 : 2);
+    const int64_t target = (int64_t)sep2d_num_sms() * PER_SM * FWD_WAVES_;
     int chunks = (int)std::max<int64_t>(1, target / (a.tiles1 * nbatch));   // (rounded down: whole waves)
     int CR = (a.n2 + chunks - 1) / chunks;
     CR = std::min(FWD_MAXCR, std::max(8, (CR + 7) & ~7));
