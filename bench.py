@@ -39,6 +39,20 @@ METRIC = "Gsamples/s fwd+adjoint, 2D separable Lanczos-4 (fraction of HBM roofli
 WORKLOAD = "2D separable TabulatedInterpolator Lanczos-4, Float32 4096^2->8192^2, forward + adjoint"
 
 
+def common_config():
+    """The `config` object both arms print (identical dicts, so the driver can compare them)."""
+    return {"workload": WORKLOAD, "alpha": 1, "beta": 0, "images_per_gpu": 1}
+
+
+def host_threads() -> int:
+    """Threads the CPU arm uses: every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it
+    to 1 for N > 1, which made the round-1 ratios incomparable across N)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -122,7 +136,7 @@ def run_reference(args):
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import li_oracle as O
-    nthreads = O.max_threads()
+    nthreads = host_threads()
     rng = np.random.default_rng(0xB200)
     x = np.linspace(1.0, float(M), N_OUT)
     J, W = O.maketable(O.kernel(O.LANCZOS, S), x, M, np.float32)
@@ -131,7 +145,7 @@ def run_reference(args):
     # bound the whole run to a few minutes: calibrate on one step
     t_one, _, _ = cpu_reference_step(O, J, W, src, y, nthreads)
     steps, warmup = args.steps, args.warmup
-    budget = 150.0
+    budget = 120.0
     if t_one * (steps + warmup) > budget:
         steps = max(1, int(budget / t_one) - 1)
         warmup = min(warmup, 1)
@@ -143,18 +157,99 @@ def run_reference(args):
         total += dt
     ms = 1e3 * total / steps
     value = SAMPLES_PER_STEP / (ms * 1e-3) / 1e9
+    # the reference itself is single-threaded (no Threads.@threads anywhere in /root/reference/src): one step on one core
+    t_single, _, _ = cpu_reference_step(O, J, W, src, y, 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "schedule": "two passes per apply, as the reference composes A1*A2",
-                   "note": "CPU restatement of the reference loops (oracle/); Julia is not installed in this image"},
+        "config": common_config(),
+        "notes": {"schedule": "two passes per apply, as the reference composes A1*A2",
+                  "what": "CPU restatement of the reference loops (oracle/); Julia is not installed in this image",
+                  "threads": f"{nthreads} OpenMP threads (all cores of the box, independent of OMP_NUM_THREADS)",
+                  "single_thread_value": SAMPLES_PER_STEP / t_single / 1e9,
+                  "single_thread_note": "1 thread = what the single-threaded reference does; 1 full-size step"},
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": nthreads, "kind": "port",
                          "sample": f"full workload, {steps} steps (requested {args.steps})"},
         "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_multi(li, torch, dist, rank, world, dev, frames_total=512, reps=5):
+    """BASELINE.json config #5, strong scaling: the adjoint of `frames_total` observed 2048^2 frames (per-frame
+    Lanczos-6 SafeFlat interpolators, shifts U(-8, 8)) accumulated into ONE shared 2048^2 model.  Frames are
+    block-sharded over the ranks; every rank makes ONE call of the C ABI's li_adjoint_accumulate_allreduce (multi-frame
+    accumulate kernel, model produced in 4 bands, NCCL all-reduce of each band on the library's own communicator
+    overlapping the next band).  Times: CUDA events, max over ranks.  `allreduce_ms_exposed` = that time minus the
+    time of the same local work without a communicator."""
+    T = np.float32
+    m = 2048
+    lo, hi = li.shard_range(frames_total, rank, world)
+    ker = li.SafeFlat(li.LanczosKernel(T, 6))
+    xs = np.arange(1, m + 1, dtype=np.float64)
+    shifts = np.random.default_rng(5).uniform(-8, 8, (frames_total, 2))
+    tabs = []
+    for k in range(lo, hi):
+        tabs.append((li.TabulatedInterpolator(T, 1, ker, xs + shifts[k, 0], m).table,
+                     li.TabulatedInterpolator(T, 2, ker, xs + shifts[k, 1], m).table))
+    frames = li.device_empty((m, m, hi - lo), T, dev)
+    frames.normal_(generator=torch.Generator(device=dev).manual_seed(505 + rank))
+    views = [frames[:, :, k] for k in range(hi - lo)]
+    model = li.device_empty((m, m), T, dev)
+    comm = li.Comm.from_torch_distributed() if world > 1 else None
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(reps):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t.item()))
+        return min(ts), float(np.median(ts))
+
+    l0 = li.launch_count()
+    li.adjoint_accumulate(tabs, views, model, comm=comm, nbands=4)
+    torch.cuda.synchronize()
+    launches = li.launch_count() - l0        # (includes the one-off table analysis of the first call)
+    l0 = li.launch_count()
+    li.adjoint_accumulate(tabs, views, model, comm=comm, nbands=4)
+    launches = li.launch_count() - l0
+    t_all, t_all_med = timed(lambda: li.adjoint_accumulate(tabs, views, model, comm=comm, nbands=4))
+    t_loc, t_loc_med = timed(lambda: li.adjoint_accumulate(tabs, views, model, comm=None))
+    # the per-frame path of round 1 (one launch per frame), for the record
+    li.set_option("no_multi", 1)
+    try:
+        t_old, _ = timed(lambda: li.adjoint_accumulate(tabs, views, model, comm=None))
+    finally:
+        li.set_option("no_multi", 0)
+    finite = bool(torch.isfinite(model).all().item())
+    peak, _ = measured_peak_gbs()
+    nloc = hi - lo
+    algo = nloc * m * m * 4 + m * m * 4 + nloc * 2 * m * (4 + 4 * 6)     # local frames + model + tables (base + W)
+    if comm is not None:
+        comm.destroy()
+    return {"workload": f"config #5: adjoint of {frames_total} x 2048^2 frames (Lanczos-6, SafeFlat, shifts +-8) into one shared "
+                        f"2048^2 model; frames sharded over {world} GPU(s); NCCL all-reduce inside libli_b200.so, 4 bands",
+            "scaling": "strong", "n_gpus": world, "frames": frames_total, "frames_per_gpu": nloc,
+            "ms": t_all, "ms_median": t_all_med, "ms_local_only": t_loc, "allreduce_ms_exposed": max(0.0, t_all - t_loc),
+            "us_per_frame_local": 1e3 * t_loc / max(nloc, 1), "ms_one_launch_per_frame": t_old,
+            "Gsamples_s": frames_total * m * m / (t_all * 1e-3) / 1e9,
+            "frac": algo / (t_loc * 1e-3) / 1e9 / peak, "achieved_gbs_local": algo / (t_loc * 1e-3) / 1e9,
+            "algorithmic_bytes_per_gpu": algo, "kernel": "sep2d_adj_multi_kernel", "launches_per_step": int(launches),
+            "allreduce_bytes": m * m * 4, "results_finite": finite}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -304,12 +399,22 @@ def run_b200(args):
     e2e_value = world * SAMPLES_PER_STEP / e2e_s / 1e9
     e2e_ok = bool(np.isfinite(yh[::997, ::991]).all() and np.isfinite(zh[::97, ::91]).all())
 
+    # ---- config #5 (the path's one collective), through the C ABI; every rank takes part
+    multi = None
+    if not args.no_multi:
+        del xs, ys_in, ys_out, zs
+        torch.cuda.empty_cache()
+        try:
+            multi = run_multi(li, torch, dist, rank, world, dev, frames_total=args.frames)
+        except Exception as exc:  # pragma: no cover - reported, never hidden
+            multi = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- CPU baseline on rank 0 (bounded sample: one full-size step, all host threads)
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import li_oracle as O
-        nthreads = O.max_threads()
+        nthreads = host_threads()
         J, W = O.maketable(O.kernel(O.LANCZOS, S), np.linspace(1.0, float(M), N_OUT), M, np.float32)
         y_np = np.asfortranarray(np.ones((N_OUT, N_OUT), dtype=np.float32))
         dt, out_ref, back_ref = cpu_reference_step(O, J, W, np.asarray(xh), y_np, nthreads)
@@ -325,23 +430,25 @@ def run_b200(args):
         dom_ms, dom = (adj_ms, "sep2d_adj_stream_kernel") if adj_ms >= fwd_ms else (fwd_ms, "sep2d_fwd_kernel")
         achieved = ALGO_BYTES_PER_APPLY / (dom_ms * 1e-3) / 1e9
         # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), if any
-        traffic = None
+        traffic, traffic_from = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(dom)
+                tj = json.load(f)
+            traffic, traffic_from = tj.get(dom), tj.get("captured_at")
         except (OSError, ValueError):
             pass
         line = {
             "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "alpha": 1, "beta": 0, "images_per_gpu": 1,
-                       "l2": "inputs rotate over 2 buffer sets of 671 MB each (> 126 MB L2); no timed kernel re-reads fresh data",
-                       "timed_region": timed_how, "eager_ms_per_step": eager_ms_per_step,
-                       "per_launch_times": "CUDA events around each apply in the eager pass of the same K steps",
-                       "host_wall_ms_per_step": 1e3 * t_host / args.steps},
+            "config": common_config(),
+            "notes": {"l2": "inputs rotate over 2 buffer sets of 671 MB each (> 126 MB L2); no timed kernel re-reads fresh data",
+                      "timed_region": timed_how, "eager_ms_per_step": eager_ms_per_step,
+                      "per_launch_times": "CUDA events around each apply in the eager pass of the same K steps",
+                      "host_wall_ms_per_step": 1e3 * t_host / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_captured_at": traffic_from,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_APPLY,
                          "fwd_ms": fwd_ms, "adj_ms": adj_ms,
                          "fwd_frac": ALGO_BYTES_PER_APPLY / (fwd_ms * 1e-3) / 1e9 / peak,
@@ -355,6 +462,7 @@ def run_b200(args):
                     "blocking_value": world * SAMPLES_PER_STEP / e2e_blocking_s / 1e9, "results_finite": e2e_ok},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "multi": multi,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -369,6 +477,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-multi", action="store_true", help="skip the config #5 block (multi-frame accumulate + all-reduce)")
+    ap.add_argument("--frames", type=int, default=512, help="frames of the config #5 block (all GPUs together)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

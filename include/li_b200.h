@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define LI_B200_VERSION 100 /* 0.1.0 */
+#define LI_B200_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define LI_API __attribute__((visibility("default")))
@@ -49,7 +49,8 @@ typedef enum {
     LI_ERR_BOUNDS = 4,      /* "out of bound index in interpolation table" (src/tabulated.jl:212) */
     LI_ERR_UNSUPPORTED = 5, /* kernel family / size not built */
     LI_ERR_CUDA = 6,
-    LI_ERR_NOMEM = 7
+    LI_ERR_NOMEM = 7,
+    LI_ERR_NCCL = 8         /* NCCL missing (dlopen of libnccl.so.2 failed) or a collective failed */
 } li_status;
 
 typedef enum { LI_F32 = 0, LI_F64 = 1 } li_dtype;
@@ -225,6 +226,77 @@ LI_API int li_tab_apply_host_async(int adjoint, const li_table *t, int64_t npre,
 LI_API int li_sep_apply_host_async(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other,
                                    int64_t nbatch, double alpha, const void *src_host, double beta,
                                    void *dst_host, int variant, void *stream);
+
+/* ---- many frames accumulated into one model; the all-reduce over the GPUs of a node ----------------------------
+ * Iterative fitting (README.md:36-37) evaluates  model <- beta*model + alpha * sum_k H_k' y_k  with H_k = A1_k * A2_k
+ * the 2-D separable operator of frame k (composition of test/benchmarks.jl:27-29; adjoint loops
+ * src/tabulated.jl:441-478).  The reference runs `apply!(alpha, Adjoint, H_k, y_k, false, 1, model)` frame after
+ * frame on one core; here the local frames go through ONE multi-frame kernel and, with a communicator, the frames
+ * are sharded over the ranks (one rank per GPU) and the rank-private sums are combined with an NCCL all-reduce
+ * over NVLink -- the one exchange step of the path.  NCCL is loaded with dlopen at the first li_comm_* call. */
+typedef struct li_comm li_comm;
+#define LI_COMM_ID_BYTES 128
+/* rank 0 creates an id and hands it to the other ranks by any out-of-band means (MPI, a file, torch.distributed) */
+LI_API int li_comm_unique_id(void *id, size_t bytes);
+/* one rank per GPU (one process, or one host thread, per GPU); binds to the CURRENT device; collective call */
+LI_API int li_comm_init_rank(const void *id, int nranks, int rank, li_comm **out);
+/* one process driving `ndev` GPUs (devices == NULL: 0..ndev-1): out[k] is the communicator of devices[k].
+ * Use one host thread per device for the calls below, or bracket them with li_comm_group_start/end
+ * (li_allreduce_sum only: li_adjoint_accumulate_allreduce must not be called inside a group). */
+LI_API int li_comm_init_all(int ndev, const int *devices, li_comm **out);
+LI_API int li_comm_info(const li_comm *comm, int *rank, int *nranks, int *device);
+LI_API int li_comm_destroy(li_comm *comm);
+LI_API int li_comm_group_start(void);
+LI_API int li_comm_group_end(void);
+LI_API int li_nccl_version(int *version);
+/* buf <- sum over the ranks of buf (in place, `count` elements); comm == NULL or a single rank: no-op */
+LI_API int li_allreduce_sum(li_comm *comm, int dtype, void *buf_dev, int64_t count, void *stream);
+/* model[m1, m2] <- beta*model + alpha * sum over ALL ranks of sum over the nframes LOCAL frames of H_k' y_k.
+ * tabs[2k], tabs[2k+1] are the dim-1 / dim-2 tables of local frame k (ncols = m1 / m2), src_dev[k] its data
+ * [nrows_1, nrows_2].  comm == NULL: this GPU only.  A rank may own zero frames.  The model is produced in `nbands`
+ * bands of rows; the all-reduce of a band overlaps the computation of the next one (nbands <= 16; 1 = a single
+ * all-reduce at the end).  Deterministic for a given number of ranks, bands and frame order.  Asynchronous on
+ * `stream` (the communicator's own stream is joined back into it before the call returns). */
+LI_API int li_adjoint_accumulate_allreduce(li_comm *comm, int dtype, int64_t m1, int64_t m2, int64_t nframes,
+                                           const li_table *const *tabs, const void *const *src_dev, double alpha,
+                                           double beta, void *model_dev, int nbands, void *stream);
+
+/* ---- vectors and the linear conjugate-gradient driver ------------------------------------------------------------
+ * LazyAlgebra's vdot / vupdate! / vcombine! and conjgrad as used by `x = conjgrad(H'*H, H'*y; ftol, maxiter)`
+ * (test/benchmarks.jl:31-40).  Dot products are accumulated in Float64 in a fixed order (deterministic). */
+LI_API int li_vdot(int dtype, const void *x_dev, const void *y_dev, int64_t n, double *result_host, void *stream); /* blocking */
+LI_API int li_vdot_async(int dtype, const void *x_dev, const void *y_dev, int64_t n, double *result_dev, void *stream);
+LI_API int li_vupdate(int dtype, void *y_dev, double alpha, const void *x_dev, int64_t n, void *stream); /* y += alpha*x */
+/* dst <- alpha*x + beta*y (dst may alias x or y; beta == 0 never reads y) */
+LI_API int li_vcombine(int dtype, void *dst_dev, double alpha, const void *x_dev, double beta, const void *y_dev,
+                       int64_t n, void *stream);
+typedef int (*li_apply_fn)(void *ctx, const void *x_dev, void *y_dev, void *stream); /* y <- A*x, returns an li_status */
+typedef struct {
+    int32_t maxiter;     /* default 50 */
+    int32_t check_every; /* the host reads the residual every so many iterations (default 5); no other round trip */
+    double ftol;         /* stop when the decrease of the objective, alpha*rho/2, is <= ftol * its largest value */
+    double gtol_abs, gtol_rel; /* stop when sqrt(rho) <= max(gtol_abs, gtol_rel*sqrt(rho0)), rho = |b - A*x|^2 */
+} li_cg_options;
+typedef enum { LI_CG_MAXITER = 0, LI_CG_FTEST = 1, LI_CG_GTEST = 2, LI_CG_NOT_POSITIVE = 3 } li_cg_status;
+typedef struct {
+    int32_t iters, status; /* li_cg_status */
+    double rho0, rho;      /* squared residual norm at the start / at the last check */
+} li_cg_info;
+/* solves A*x = b for a symmetric positive (semi-)definite A given as a callback; x_is_zero != 0 starts from x = 0 */
+LI_API int li_conjgrad(li_apply_fn A, void *ctx, int dtype, int64_t n, const void *b_dev, void *x_dev, int x_is_zero,
+                       const li_cg_options *opts, li_cg_info *info, void *stream);
+/* x <- argmin |H*x - y|^2 + mu*|x|^2 for the separable operator H = A_1*...*A_ndim of li_sep_apply: conjugate
+ * gradients on (H'*H + mu*I) x = H'*y entirely inside the library (no callback into the host language) */
+LI_API int li_conjgrad_sep(int ndim, const li_table *const *tabs, const int64_t *dims_other, int64_t nbatch, double mu,
+                           const void *y_dev, void *x_dev, int x_is_zero, const li_cg_options *opts, li_cg_info *info,
+                           void *stream);
+
+/* ---- dispatch switches ------------------------------------------------------
+ * Process-wide integer options, initialised once from the environment at load time (LI_B200_<NAME>): "no_fused",
+ * "no_stream_dn", "no_bands", "affine_plain", "trace", "adj_debug", "no_multi".  They select slower cross-check
+ * paths; the hot path never calls getenv(). */
+LI_API int li_set_option(const char *name, int value);
+LI_API int li_get_option(const char *name, int *value);
 
 /* ---- counters --------------------------------------------------------------
  * Number of CUDA kernels this library has launched in this process (all entry

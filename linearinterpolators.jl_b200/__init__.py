@@ -9,7 +9,7 @@ not been built -- there is no CPU fallback.
 from . import _lib
 from ._arrays import DeviceArray, HostStream, async_host, device_empty, pinned_empty, to_device, to_host
 from ._lib import (ArgumentError, CudaError, DimensionMismatch, ErrorException, InexactError, LIB_PATH,
-                   VARIANT_ATOMIC, VARIANT_AUTO, VARIANT_GATHER, launch_count)
+                   VARIANT_ATOMIC, VARIANT_AUTO, VARIANT_GATHER, get_option, launch_count, set_option)
 from .kernels import (Boundaries, CardinalCubicSpline, CatmullRomSpline, CubicSpline, Flat, Kernel, KeysSpline,
                       LanczosKernel, LinearSpline, MitchellNetravaliSpline, QuadraticSpline, RectangularSpline,
                       SafeFlat, boundaries)
@@ -20,7 +20,8 @@ from .separable import sep2d_otf_apply, sep_apply_batch, sep_apply_tables
 from .sparse import Range, SparseInterpolator, SparseUnidimensionalInterpolator, fractional_index
 from .tabulated import TabulatedInterpolator, coefficients, columns, ncols, nrows, width
 from .unidimensional import otf1d_apply
-from .distributed import accumulate_adjoint, shard_range, world_info
+from .distributed import Comm, accumulate_adjoint, adjoint_accumulate, shard_range, world_info
+from .solvers import CgResult, conjgrad, fit_separable, vcombine, vdot_device, vupdate
 
 
 def getcoefs(ker, length, x):

@@ -49,6 +49,17 @@ class DeviceArray:
         p = C.c_void_p()
         _lib.check(_lib.lib.li_malloc(C.byref(p), self.nbytes))
         self.ptr = p.value or 0
+        self._owns = True
+
+    @classmethod
+    def view(cls, ptr: int, shape, dtype) -> "DeviceArray":
+        """Non-owning column-major view of device memory (e.g. a buffer handed to a callback by the library)."""
+        d = object.__new__(cls)
+        d.shape = tuple(int(s) for s in shape)
+        d.dtype = np.dtype(dtype)
+        d.nbytes = int(np.prod(d.shape, dtype=np.int64)) * d.dtype.itemsize
+        d.ptr, d._owns = int(ptr), False
+        return d
 
     @classmethod
     def from_numpy(cls, a: np.ndarray, stream=0) -> "DeviceArray":
@@ -66,9 +77,9 @@ class DeviceArray:
 
     def __del__(self):
         try:
-            if getattr(self, "ptr", 0):
+            if getattr(self, "ptr", 0) and getattr(self, "_owns", True):
                 _lib.lib.li_free(self.ptr)
-                self.ptr = 0
+            self.ptr = 0
         except Exception:  # pragma: no cover
             pass
 
@@ -194,6 +205,21 @@ def to_device(a, device=None):
         src = torch.from_numpy(np.ascontiguousarray(a.T))  # same bytes as the column-major array
         d.permute(*reversed(range(a.ndim))).copy_(src) if a.ndim > 1 else d.copy_(src)
     return d
+
+
+def wrap_device_ptr(ptr: int, shape, dtype, like):
+    """Column-major device array of the same kind as ``like`` over raw device memory (non-owning)."""
+    shape = tuple(int(s) for s in shape)
+    dtype = np.dtype(dtype)
+    if is_torch(like):
+        class _Ext:
+            pass
+        e = _Ext()
+        n = int(np.prod(shape, dtype=np.int64))
+        e.__cuda_array_interface__ = {"shape": (n,), "typestr": dtype.str, "data": (int(ptr), False), "version": 2}
+        t = torch.as_tensor(e, device=like.device)
+        return t.view(shape[::-1]).permute(*reversed(range(len(shape)))) if len(shape) > 1 else t
+    return DeviceArray.view(ptr, shape, dtype)
 
 
 def to_host(x) -> np.ndarray:

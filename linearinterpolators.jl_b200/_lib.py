@@ -11,7 +11,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libli_b200.so")
 
-OK, ERR_ARG, ERR_DIM, ERR_INEXACT, ERR_BOUNDS, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = range(8)
+OK, ERR_ARG, ERR_DIM, ERR_INEXACT, ERR_BOUNDS, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_NCCL = range(9)
+COMM_ID_BYTES = 128
+CG_MAXITER, CG_FTEST, CG_GTEST, CG_NOT_POSITIVE = range(4)
 F32, F64 = 0, 1
 FLAT, SAFEFLAT = 0, 1
 VARIANT_AUTO, VARIANT_GATHER, VARIANT_ATOMIC = 0, 1, 2
@@ -29,6 +31,20 @@ class TableInfo(C.Structure):
     """``li_table_info``."""
     _fields_ = [("dtype", C.c_int32), ("S", C.c_int32), ("nrows", C.c_int64), ("ncols", C.c_int64),
                 ("windowed", C.c_int32), ("monotone", C.c_int32)]
+
+
+class CgOptions(C.Structure):
+    """``li_cg_options``."""
+    _fields_ = [("maxiter", C.c_int32), ("check_every", C.c_int32), ("ftol", C.c_double), ("gtol_abs", C.c_double),
+                ("gtol_rel", C.c_double)]
+
+
+class CgInfo(C.Structure):
+    """``li_cg_info``."""
+    _fields_ = [("iters", C.c_int32), ("status", C.c_int32), ("rho0", C.c_double), ("rho", C.c_double)]
+
+
+APPLY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)   # li_apply_fn
 
 
 # ---- exceptions mirroring the reference's (SURVEY.md §5 "Argument validation") ----------------
@@ -108,6 +124,26 @@ _PROTOS = {
     "li_sep_apply_host_async": (_int, [_int, _int, C.POINTER(_vp), C.POINTER(_i64), _i64, _dbl, _vp, _dbl, _vp, _int,
                                        _vp]),
     "li_kernel_launch_count": (_i64, []),
+    "li_set_option": (_int, [C.c_char_p, _int]),
+    "li_get_option": (_int, [C.c_char_p, C.POINTER(_int)]),
+    "li_comm_unique_id": (_int, [_vp, _sz]),
+    "li_comm_init_rank": (_int, [_vp, _int, _int, C.POINTER(_vp)]),
+    "li_comm_init_all": (_int, [_int, C.POINTER(_int), C.POINTER(_vp)]),
+    "li_comm_info": (_int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
+    "li_comm_destroy": (_int, [_vp]),
+    "li_comm_group_start": (_int, []),
+    "li_comm_group_end": (_int, []),
+    "li_nccl_version": (_int, [C.POINTER(_int)]),
+    "li_allreduce_sum": (_int, [_vp, _int, _vp, _i64, _vp]),
+    "li_adjoint_accumulate_allreduce": (_int, [_vp, _int, _i64, _i64, _i64, C.POINTER(_vp), C.POINTER(_vp), _dbl, _dbl, _vp,
+                                               _int, _vp]),
+    "li_vdot": (_int, [_int, _vp, _vp, _i64, C.POINTER(_dbl), _vp]),
+    "li_vdot_async": (_int, [_int, _vp, _vp, _i64, _vp, _vp]),
+    "li_vupdate": (_int, [_int, _vp, _dbl, _vp, _i64, _vp]),
+    "li_vcombine": (_int, [_int, _vp, _dbl, _vp, _dbl, _vp, _i64, _vp]),
+    "li_conjgrad": (_int, [APPLY_FN, _vp, _int, _i64, _vp, _vp, _int, C.POINTER(CgOptions), C.POINTER(CgInfo), _vp]),
+    "li_conjgrad_sep": (_int, [_int, C.POINTER(_vp), C.POINTER(_i64), _i64, _dbl, _vp, _vp, _int, C.POINTER(CgOptions),
+                               C.POINTER(CgInfo), _vp]),
 }
 for _name, (_res, _args) in _PROTOS.items():
     _f = getattr(lib, _name)  # AttributeError here == the .so does not export the declared ABI
@@ -136,7 +172,20 @@ def check(status: int) -> None:
         raise NotImplementedError(msg)
     if status == ERR_NOMEM:
         raise MemoryError(msg)
+    if status == ERR_NCCL:
+        raise CudaError(f"LI_ERR_NCCL: {msg}")
     raise CudaError(f"{lib.li_status_string(status).decode()}: {msg}")
+
+
+def set_option(name: str, value: int) -> None:
+    """``li_set_option``: process-wide dispatch switch (e.g. ``set_option("no_fused", 1)`` for the cross-check path)."""
+    check(lib.li_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    v = C.c_int()
+    check(lib.li_get_option(name.encode(), C.byref(v)))
+    return int(v.value)
 
 
 def launch_count() -> int:

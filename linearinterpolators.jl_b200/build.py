@@ -18,7 +18,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libli_b200.so")
 
-SOURCES = ["li_api.cu", "li_table.cu", "li_tab_apply.cu", "li_sep.cu", "li_sep2d.cu", "li_sep2d_adjs_f32.cu", "li_sep2d_adjs_f64.cu", "li_affine.cu", "li_affine_f32.cu", "li_affine_f64.cu"]
+SOURCES = ["li_api.cu", "li_table.cu", "li_tab_apply.cu", "li_sep.cu", "li_sep2d.cu", "li_sep2d_adjs_f32.cu", "li_sep2d_adjs_f64.cu", "li_affine.cu", "li_affine_f32.cu", "li_affine_f64.cu",
+           "li_sep2d_multi_f32.cu", "li_sep2d_multi_f64.cu", "li_comm.cu", "li_vec.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -74,7 +75,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 raise RuntimeError(f"nvcc failed on {cmd[-3]}")
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout)

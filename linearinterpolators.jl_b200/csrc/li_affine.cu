@@ -24,7 +24,7 @@ extern "C" int li_affine2d_apply(int adjoint, const li_kernel_desc *ker1, const 
     // direct: LI_VARIANT_AUTO = tiled kernel (source boxes staged in shared memory), LI_VARIANT_ATOMIC = one thread
     // per pixel straight on global memory (the first implementation, kept for comparison); the adjoint is the
     // atomic scatter in both cases
-    const bool tiled = !adjoint && variant != LI_VARIANT_ATOMIC && !getenv("LI_B200_AFFINE_PLAIN");
+    const bool tiled = !adjoint && variant != LI_VARIANT_ATOMIC && !li::opt(li::OPT_AFFINE_PLAIN);
     LI_REQUIRE(ker1 && ker2 && R && dst_dev, LI_ERR_ARG, "null argument");
     LI_REQUIRE(ker1->dtype == ker2->dtype, LI_ERR_ARG, "kernels must share one floating-point type");
     LI_REQUIRE(n1 >= 0 && n2 >= 0 && m1 >= 1 && m2 >= 1 && nbatch >= 0, LI_ERR_DIM, "bad dimensions");
@@ -41,7 +41,8 @@ extern "C" int li_affine2d_apply(int adjoint, const li_kernel_desc *ker1, const 
         int rc = li::vscale_impl(dtype, dst_dev, nout, beta, st);  // :236
         if (rc != LI_OK) return rc;
     }
-    static thread_local int *d_err = nullptr;
+    static thread_local std::map<int, int *> d_errs;   // per device
+    int *&d_err = d_errs[li::current_device()];
     if (!d_err) LI_CUDA(cudaMalloc(&d_err, sizeof(int)));
     LI_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
     int rc = dtype == LI_F32 ? li::affine_T<float>(adjoint, ker1, ker2, R, n1, n2, m1, m2, nbatch, alpha, src_dev,

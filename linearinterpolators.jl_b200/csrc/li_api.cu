@@ -1,5 +1,6 @@
 // li_api.cu -- library plumbing: errors, device, memory, vscale!, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "li_common.cuh"
 
@@ -7,6 +8,29 @@ namespace li {
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_options[OPT_COUNT];
+
+static const char *const kOptionNames[OPT_COUNT] = {"no_fused", "no_stream_dn", "no_bands", "affine_plain",
+                                                    "trace", "adj_debug", "no_multi"};
+static const char *const kOptionEnv[OPT_COUNT] = {"LI_B200_NO_FUSED", "LI_B200_NO_STREAM_DN", "LI_B200_NO_BANDS",
+                                                  "LI_B200_AFFINE_PLAIN", "LI_B200_TRACE", "LI_B200_ADJ_DEBUG",
+                                                  "LI_B200_NO_MULTI"};
+// the environment is consulted once, at load time
+static const bool g_options_init = [] {
+    for (int k = 0; k < OPT_COUNT; ++k) {
+        const char *v = getenv(kOptionEnv[k]);
+        g_options[k].store(v ? (atoi(v) ? atoi(v) : 1) : 0);
+    }
+    return true;
+}();
+
+static int option_index(const char *name)
+{
+    if (name)
+        for (int k = 0; k < OPT_COUNT; ++k)
+            if (!strcmp(name, kOptionNames[k])) return k;
+    return -1;
+}
 
 void set_error(const char *fmt, ...)
 {
@@ -45,14 +69,18 @@ int vscale_impl(int dtype, void *y, int64_t n, double beta, cudaStream_t st)
 // cudaMalloc/cudaFree per call would dominate small applies and serialise the device, and calls on different
 // streams must not share buffers.
 struct StageSet {
-    void *ptr[4] = {nullptr, nullptr, nullptr, nullptr};   // 0: src, 1: dst, 2: workspace, 3: partial accumulators
-    size_t bytes[4] = {0, 0, 0, 0};
+    // 0: src, 1: dst, 2: workspace, 3: partial accumulators, 4: frame pointers, 5: partial models of frame groups,
+    // 6: rank-private accumulator of the all-reduce, 7: spare
+    void *ptr[8] = {};
+    size_t bytes[8] = {};
 };
-static thread_local std::map<void *, StageSet> g_stage;
+static thread_local std::map<std::pair<int, void *>, StageSet> g_stage;   // key: (device, stream)
 
 int staging(int slot, size_t bytes, void **out, void *stream_key)
 {
-    StageSet &s = g_stage[stream_key];
+    int dev = 0;
+    LI_CUDA(cudaGetDevice(&dev));
+    StageSet &s = g_stage[std::make_pair(dev, stream_key)];
     if (bytes > s.bytes[slot]) {
         if (s.ptr[slot]) {
             cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream_key));   // nothing in flight may still use it
@@ -87,6 +115,7 @@ const char *li_status_string(int status)
     case LI_ERR_UNSUPPORTED: return "LI_ERR_UNSUPPORTED";
     case LI_ERR_CUDA: return "LI_ERR_CUDA";
     case LI_ERR_NOMEM: return "LI_ERR_NOMEM";
+    case LI_ERR_NCCL: return "LI_ERR_NCCL";
     default: return "LI_ERR_UNKNOWN";
     }
 }
@@ -199,5 +228,21 @@ int li_vscale(int dtype, void *y_dev, int64_t n, double beta, void *stream)
 }
 
 int64_t li_kernel_launch_count(void) { return (int64_t)li::g_launches.load(); }
+
+int li_set_option(const char *name, int value)
+{
+    const int k = li::option_index(name);
+    LI_REQUIRE(k >= 0, LI_ERR_ARG, "unknown option '%s'", name ? name : "(null)");
+    li::g_options[k].store(value);
+    return LI_OK;
+}
+
+int li_get_option(const char *name, int *value)
+{
+    const int k = li::option_index(name);
+    LI_REQUIRE(k >= 0 && value, LI_ERR_ARG, "unknown option '%s'", name ? name : "(null)");
+    *value = li::g_options[k].load();
+    return LI_OK;
+}
 
 }  // extern "C"

@@ -19,6 +19,22 @@ extern std::atomic<long long> g_launches;
 
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Process-wide switches of the dispatch (li_set_option / li_get_option).  Read from the environment ONCE, when the
+// library is loaded (LI_B200_NO_FUSED, LI_B200_NO_STREAM_DN, LI_B200_NO_BANDS, LI_B200_AFFINE_PLAIN, LI_B200_TRACE,
+// LI_B200_ADJ_DEBUG); the hot path only reads these atomics, never getenv().
+enum Option {
+    OPT_NO_FUSED = 0,      // fused 2-D kernels off: per-dimension passes (cross-check of the fused kernels)
+    OPT_NO_STREAM_DN,      // streaming / window kernels of li_tab_apply off: generic gather kernels
+    OPT_NO_BANDS,          // host-buffer pipeline off: upload, apply, download
+    OPT_AFFINE_PLAIN,      // affine operators: one thread per pixel on global memory
+    OPT_TRACE,             // print dispatch decisions to stderr
+    OPT_ADJ_DEBUG,         // timing probes of the fused adjoint (see li_sep2d.cu)
+    OPT_NO_MULTI,          // multi-frame accumulate kernel off: one launch per frame
+    OPT_COUNT
+};
+extern std::atomic<int> g_options[OPT_COUNT];
+inline int opt(Option o) { return g_options[o].load(std::memory_order_relaxed); }
+
 #define LI_CUDA(expr)                                                                      \
     do {                                                                                   \
         cudaError_t e__ = (expr);                                                          \
@@ -43,6 +59,12 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
         }                                                                                  \
     } while (0)
 
+inline int current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
 inline size_t dtype_size(int dtype) { return dtype == LI_F32 ? 4 : 8; }
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -56,6 +78,7 @@ struct AdjointIndex;
 struct li_table {
     int32_t dtype = 0, S = 0;
     int64_t nrows = 0, ncols = 0;
+    uint64_t uid = 0;         // unique per table of this process (plan caches key on it: pointers get reused)
     int32_t *J = nullptr;     // [nrows*S], 0-based, clamped
     void *W = nullptr;        // [nrows*S], T
     int32_t *base = nullptr;  // [nrows] canonical window base (0-based tap s is clamp(base+s)); valid iff windowed

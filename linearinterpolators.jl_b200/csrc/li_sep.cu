@@ -5,6 +5,7 @@
 // (test/benchmarks.jl:27-29,44-49; H*x = A_1*(...*(A_n*x)), H'*y = A_n'*(...*(A_1'*y)))
 // and the on-the-fly operators src/unidimensional.jl:95-245, src/separable.jl:56-162.
 #include <algorithm>
+#include <map>
 #include <vector>
 
 #include "li_common.cuh"
@@ -144,6 +145,9 @@ static int sep_apply_impl(int adjoint, int ndim, const li_table *const *tabs, co
 
 namespace li {
 
+int sep_accumulate_multi(int64_t n, const li_table *const *tabs, const void *const *src_dev, double alpha, double beta,
+                         void *dst, int64_t row_lo, int64_t row_hi, cudaStream_t st, bool *done);   // li_comm.cu
+
 template <typename T>
 __global__ void sum_partials_kernel(T *__restrict__ dst, const T *__restrict__ part, int64_t n, int np)
 {
@@ -169,7 +173,25 @@ int sep_accumulate_concurrent(int adjoint, int ndim, int64_t n, const li_table *
     constexpr int NSTR = 4;
     *ndone = 0;
     // (beta must be 1: with any other value the in-order semantics rescales the sum at every frame)
-    if (ndim != 2 || n < 2 * NSTR || variant == LI_VARIANT_ATOMIC || alpha == 0.0 || beta != 1.0) return LI_OK;
+    if (ndim != 2 || n < 2 || variant == LI_VARIANT_ATOMIC || alpha == 0.0 || beta != 1.0) return LI_OK;
+    // adjoints into one destination: the multi-frame accumulate kernel (li_sep2d_multi.cuh), one launch for the batch
+    if (adjoint && nbatch == 1) {
+        bool same = true, full = true;
+        for (int64_t k = 0; k < n && same; ++k) {
+            same = dst_dev[k] == dst_dev[0];
+            full = full && tabs[2 * k] && tabs[2 * k + 1];
+        }
+        if (same && full) {
+            bool done = false;
+            int rc = sep_accumulate_multi(n, tabs, src_dev, alpha, beta, dst_dev[0], 0, tabs[1]->ncols, as_stream(stream), &done);
+            if (rc != LI_OK) return rc;
+            if (done) {
+                *ndone = n;
+                return LI_OK;
+            }
+        }
+    }
+    if (n < 2 * NSTR) return LI_OK;
     for (int64_t k = 0; k < n; ++k) {
         const li_table *const *tk = tabs + k * ndim;
         if (dst_dev[k] != dst_dev[0] || !tk[0] || !tk[1] || !sep2d_fused_supported(tk[0], tk[1])) return LI_OK;
@@ -186,8 +208,15 @@ int sep_accumulate_concurrent(int adjoint, int ndim, int64_t n, const li_table *
     void *part = nullptr;
     int rc = staging(3, (size_t)(NSTR - 1) * nout * dtype_size(dtype), &part, stream);
     if (rc != LI_OK) return rc;
-    static thread_local cudaStream_t side[NSTR - 1] = {};
-    static thread_local cudaEvent_t ev_fork = nullptr, ev_join[NSTR - 1] = {};
+    struct Side {
+        cudaStream_t side[NSTR - 1] = {};
+        cudaEvent_t ev_fork = nullptr, ev_join[NSTR - 1] = {};
+    };
+    static thread_local std::map<int, Side> sides;   // per device: streams and events belong to one
+    Side &sd = sides[current_device()];
+    cudaStream_t(&side)[NSTR - 1] = sd.side;
+    cudaEvent_t &ev_fork = sd.ev_fork;
+    cudaEvent_t(&ev_join)[NSTR - 1] = sd.ev_join;
     if (!ev_fork) {
         LI_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         for (int s = 0; s < NSTR - 1; ++s) {

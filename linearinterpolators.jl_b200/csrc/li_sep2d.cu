@@ -640,12 +640,10 @@ BandCtl *&sep2d_band()
 
 int sep2d_num_sms()
 {
-    static thread_local int n = 0;
-    if (!n) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
+    static thread_local std::map<int, int> cache;   // per device
+    const int dev = current_device();
+    int &n = cache[dev];
+    if (!n && (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)) n = 148;
     return n;
 }
 
@@ -718,7 +716,7 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     constexpr int NG = ADJ_NG, PT = 2 * (ADJ_NT / NG), RG = ADJ_TD2 / NG;
     if (a.m2 < S2 || a.m1 < 2) return LI_OK;   // decline: the edge folding needs a full window inside the array
     // LI_B200_ADJ_DEBUG (timing probes): 1 = no side stream, 2 = skip the generic tile rows, 3 = tile kernels only
-    static const int dbg_mode = getenv("LI_B200_ADJ_DEBUG") ? atoi(getenv("LI_B200_ADJ_DEBUG")) : 0;
+    const int dbg_mode = opt(OPT_ADJ_DEBUG);
     if (dbg_mode != 3) {   // first choice: the streaming kernel (li_sep2d_adjs.cu); it declines what it cannot stage
         int rcs = sep2d_adj_stream<T>(a, t1, t2, nbatch, st, done);
         if (rcs != LI_OK || *done) return rcs;
@@ -767,8 +765,14 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     const int ntile_rows = a.tiles2;
     const bool beta = a.beta != (T)0;
     const size_t smem_reg = (2 * ((size_t)ADJ_TD2 * (PT / 2) + 16) + (size_t)NG * 2 * (RG + S2 - 1) * S2) * sizeof(T);
-    static thread_local cudaStream_t side = nullptr;
-    static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    struct Side {
+        cudaStream_t side = nullptr;
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    };
+    static thread_local std::map<int, Side> sides;   // per device
+    Side &sd = sides[current_device()];
+    cudaStream_t &side = sd.side;
+    cudaEvent_t &ev_fork = sd.ev_fork, &ev_join = sd.ev_join;
     const bool fork = nreg > 0 && ntile_rows - nreg > 0 && dbg_mode == 0;
     if (ntile_rows - nreg > 0 && dbg_mode != 2) {
         // the few irregular tile rows run concurrently with the regular ones on a side stream (fork / join with
@@ -856,7 +860,7 @@ int sep2d_fused_apply(int adjoint, const li_table *t1, const li_table *t2, int64
 {
     *done = false;
     if (!sep2d_fused_supported(t1, t2) || nbatch <= 0) return LI_OK;
-    if (getenv("LI_B200_NO_FUSED")) return LI_OK;
+    if (opt(OPT_NO_FUSED)) return LI_OK;
     return t1->dtype == LI_F32 ? fused_T<float>(adjoint, t1, t2, nbatch, alpha, src, beta, dst, st, done)
                                : fused_T<double>(adjoint, t1, t2, nbatch, alpha, src, beta, dst, st, done);
 }
@@ -872,8 +876,7 @@ int sep2d_host_banded(int adjoint, const li_table *t1, const li_table *t2, doubl
 {
     *done = false;
     constexpr int NBMAX = 8;
-    static const bool off = getenv("LI_B200_NO_BANDS") != nullptr;
-    if (off || !sep2d_fused_supported(t1, t2)) return LI_OK;
+    if (opt(OPT_NO_BANDS) || !sep2d_fused_supported(t1, t2)) return LI_OK;
     struct Guard {
         ~Guard() { sep2d_band() = nullptr; }
     } guard;

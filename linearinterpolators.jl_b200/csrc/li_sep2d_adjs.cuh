@@ -382,9 +382,11 @@ static int launch_stream(SepArgs<T> &a, int CR, int NRMAX, size_t smem, int64_t 
 template <typename T, int S1, int S2, int NU, int R>
 static int stream_occupancy(size_t smem)
 {
-    static thread_local int cached = 0;
+    static thread_local int cached = 0, cached_dev = -1;
     static thread_local size_t cached_smem = 0;
-    if (cached && cached_smem == smem) return cached;
+    const int dev = current_device();
+    if (cached && cached_smem == smem && cached_dev == dev) return cached;
+    cached_dev = dev;
     auto kern = sep2d_adj_stream_kernel<T, S1, S2, NU, R>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
@@ -411,7 +413,7 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     if (rc == LI_OK) rc = table_feed_rows(t1, ADS_NT, st, &span);
     if (rc != LI_OK) return rc;
     const int need = maxcount + (V - 1);
-    static const bool trace = getenv("LI_B200_TRACE") != nullptr;
+    const bool trace = opt(OPT_TRACE) != 0;
     if (need > NU_L) {   // decline (down-sampling along dim 1, or many rows hanging over an edge)
         if (trace) fprintf(stderr, "[li_b200] adj stream declines: %d taps per dst column > %d\n", need, NU_L);
         return LI_OK;
@@ -471,7 +473,7 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     a.bp2 = t2->bpf, a.W2f = (const T *)t2->Wfold, a.irrp2 = t2->irrp;
     a.F1MAX = P1;
 #ifdef ADS_ABLATE
-    if (getenv("LI_B200_ADJ_DEBUG") && atoi(getenv("LI_B200_ADJ_DEBUG")) == 4) a.vec_ok = 77;
+    if (opt(OPT_ADJ_DEBUG) == 4) a.vec_ok = 77;
 #endif
 #define LI_ADS(NUU, RR) \
     if (NU == NUU && R == RR) rc = launch_stream<T, S1, S2, NUU, RR>(a, CR, NRMAX, smem, blocks, st);

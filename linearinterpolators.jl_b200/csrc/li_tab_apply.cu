@@ -356,8 +356,7 @@ tab_adjoint_atomic_kernel(const int32_t *__restrict__ J, const T *__restrict__ W
 template <typename T, int SC>
 static int stream_vec(const li_table *t, int64_t npre, const void *src, const void *dst)
 {
-    static const bool off = getenv("LI_B200_NO_STREAM_DN") != nullptr;
-    if (SC == 0 || off || !t->windowed || !t->monotone) return 0;
+    if (SC == 0 || opt(OPT_NO_STREAM_DN) || !t->windowed || !t->monotone) return 0;
     for (int V = 16 / (int)sizeof(T); V > 1; V >>= 1)
         if (npre % V == 0 && ((uintptr_t)src) % (V * sizeof(T)) == 0 && ((uintptr_t)dst) % (V * sizeof(T)) == 0) return V;
     return 1;
@@ -494,7 +493,7 @@ static int adjoint_T(const li_table *t, int64_t npre, int64_t npost, double alph
         if (rcs != LI_OK || done) return rcs;
     }
     // contiguous dimension of a windowed monotone table: gather over the row ranges of the window table
-    if (npre == 1 && t->windowed && t->monotone && ncols >= 2 && !getenv("LI_B200_NO_STREAM_DN")) {
+    if (npre == 1 && t->windowed && t->monotone && ncols >= 2 && !opt(OPT_NO_STREAM_DN)) {
         int rcw = table_ensure_rowstart(t, st);
         if (rcw != LI_OK) return rcw;
         dim3 grid((ncols + 255) / 256, (unsigned)std::min<int64_t>(npost, 65535));
@@ -547,7 +546,7 @@ int tab_apply_impl(int adjoint, const li_table *t, int64_t npre, int64_t npost, 
     // (short vectors leave most of a 256-thread strip idle: measured break-even at a length of about 96)
     if (npre == 1 && npost >= 64 && std::max(t->nrows, t->ncols) >= 96 && t->windowed && t->monotone &&
         variant != LI_VARIANT_ATOMIC &&
-        (t->S == 2 || t->S == 3 || t->S == 4 || t->S == 6) && !getenv("LI_B200_NO_STREAM_DN")) {
+        (t->S == 2 || t->S == 3 || t->S == 4 || t->S == 6) && !opt(OPT_NO_STREAM_DN)) {
         int64_t n2 = 0;
         if (npost <= 4096) {
             n2 = npost;
@@ -557,7 +556,8 @@ int tab_apply_impl(int adjoint, const li_table *t, int64_t npre, int64_t npost, 
                     n2 = c;
                     break;
                 }
-            if (!n2 && npost <= (1LL << 22)) n2 = npost;
+            // (no divisor: the gather kernels below -- an identity table of npost rows would cost device memory
+            // per distinct batch size)
         }
         if (n2) {
             const li_table *ident = nullptr;

@@ -259,7 +259,9 @@ static int alloc_table(int dtype, int S, int64_t nrows, int64_t ncols, li_table 
     LI_REQUIRE(ncols >= 1, LI_ERR_ARG, "number of columns too small");   // src/tabulated.jl:84,96
     LI_REQUIRE(ncols <= 0x7fffffffLL && nrows * S <= 0x7fffffffLL, LI_ERR_UNSUPPORTED,
                "table too large for 32-bit device indices");
+    static std::atomic<uint64_t> next_uid{1};
     li_table *t = new li_table();
+    t->uid = next_uid.fetch_add(1);
     t->dtype = dtype;
     t->S = S;
     t->nrows = nrows;

@@ -91,3 +91,106 @@ def accumulate_adjoint(nframes: int, adjoint_into: Callable[[int, object], None]
     for part in parts[1:]:
         acc.add_(part)
     return acc
+
+
+# ---- the same exchange step behind the C ABI (NCCL inside libli_b200.so) ----------------------------------------
+class Comm:
+    """``li_comm``: an NCCL communicator owned by the library, one rank per GPU.  Nothing here needs torch; a Julia
+    or C host does the same three calls (``li_comm_unique_id`` on rank 0, hand the 128 bytes to every rank,
+    ``li_comm_init_rank`` on each)."""
+
+    def __init__(self, handle: int):
+        import ctypes as C
+        from . import _lib
+        self.handle = handle
+        r, n, d = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(_lib.lib.li_comm_info(handle, C.byref(r), C.byref(n), C.byref(d)))
+        self.rank, self.nranks, self.device = int(r.value), int(n.value), int(d.value)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from . import _lib
+        buf = (C.c_char * _lib.COMM_ID_BYTES)()
+        _lib.check(_lib.lib.li_comm_unique_id(buf, _lib.COMM_ID_BYTES))
+        return bytes(buf)
+
+    @classmethod
+    def init_rank(cls, uid: bytes, nranks: int, rank: int) -> "Comm":
+        """Collective: every rank calls it with the id made by rank 0; binds to the current CUDA device."""
+        import ctypes as C
+        from . import _lib
+        if len(uid) != _lib.COMM_ID_BYTES:
+            raise ValueError("the communicator id must be LI_COMM_ID_BYTES long")
+        h = C.c_void_p()
+        _lib.check(_lib.lib.li_comm_init_rank(uid, int(nranks), int(rank), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_torch_distributed(cls, group=None) -> Optional["Comm"]:
+        """One library communicator over the ranks of an initialised ``torch.distributed`` group (which only carries
+        the 128-byte id, over its own backend); None when there is a single process."""
+        import torch
+        import torch.distributed as dist
+        rank, world = world_info()
+        if world == 1:
+            return None
+        ids = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, group=group)
+        return cls.init_rank(ids[0], world, rank)
+
+    def allreduce_sum(self, x):
+        """In-place sum of a device array over the ranks (``li_allreduce_sum``)."""
+        import numpy as np
+        from . import _arrays as ar
+        from . import _lib
+        n = int(np.prod(ar.shape_of(x), dtype=np.int64))
+        _lib.check(_lib.lib.li_allreduce_sum(self.handle, ar.li_dtype(ar.np_dtype_of(x)), ar.data_ptr(x), n,
+                                             ar.current_stream(x)))
+        return x
+
+    def destroy(self):
+        from . import _lib
+        if getattr(self, "handle", None):
+            _lib.lib.li_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:  # pragma: no cover
+            pass
+
+
+def adjoint_accumulate(tabs_list, srcs, model, alpha=1.0, beta=0.0, comm: Optional[Comm] = None, nbands: int = 4):
+    """``model <- beta*model + alpha * sum over all ranks and local frames k of (A1_k*A2_k)' * y_k`` in one library
+    call (``li_adjoint_accumulate_allreduce``): the multi-frame accumulate kernel on the local frames, band by band,
+    with the NCCL all-reduce of each band overlapping the next band's computation.  ``tabs_list[k]`` = the two
+    per-dimension tables (``A1_k.table, A2_k.table``) of local frame k, ``srcs[k]`` its device array; ``model`` a
+    column-major device array [m1, m2].  ``comm=None``: this GPU only."""
+    import ctypes as C
+    import numpy as np
+    from . import _arrays as ar
+    from . import _lib
+    n = len(tabs_list)
+    if len(srcs) != n:
+        raise ValueError("one source array per frame")
+    if not ar.is_device(model) or not ar.is_colmajor(model) or len(ar.shape_of(model)) != 2:
+        raise _lib.ErrorException("the model must be a column-major 2-D device array")
+    dt = ar.np_dtype_of(model)
+    m1, m2 = ar.shape_of(model)
+    handles = (C.c_void_p * max(2 * n, 1))()
+    sp = (C.c_void_p * max(n, 1))()
+    for k, (tabs, x) in enumerate(zip(tabs_list, srcs)):
+        if len(tabs) != 2 or tabs[0] is None or tabs[1] is None:
+            raise _lib.ErrorException("every frame needs one table per dimension")
+        if not ar.is_device(x) or not ar.is_colmajor(x) or ar.np_dtype_of(x) != dt:
+            raise _lib.ErrorException("frames must be column-major device arrays of the model's element type")
+        if ar.shape_of(x) != (tabs[0].nrows, tabs[1].nrows):
+            raise _lib.DimensionMismatch(f"frame {k} has size {ar.shape_of(x)}, expected {(tabs[0].nrows, tabs[1].nrows)}")
+        handles[2 * k], handles[2 * k + 1] = tabs[0].handle, tabs[1].handle
+        sp[k] = ar.data_ptr(x)
+    _lib.check(_lib.lib.li_adjoint_accumulate_allreduce(comm.handle if comm is not None else None, ar.li_dtype(dt), m1, m2,
+                                                        n, handles, sp, float(alpha), float(beta), ar.data_ptr(model),
+                                                        int(nbands), ar.current_stream(model)))
+    return model

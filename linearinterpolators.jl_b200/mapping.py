@@ -160,11 +160,11 @@ class AdjointMapping(LinearMapping):
     def _flip(P):
         return Adjoint if P is Direct else Direct
 
-    def _vcreate(self, P, x):
-        return self.parent._vcreate(self._flip(P), x)
+    def _vcreate(self, P, x, **kw):      # (d=...: Tabulated without a stored dimension, src/tabulated.jl:236-257)
+        return self.parent._vcreate(self._flip(P), x, **kw)
 
-    def _apply(self, alpha, P, x, scratch, beta, y):
-        return self.parent._apply(alpha, self._flip(P), x, scratch, beta, y)
+    def _apply(self, alpha, P, x, scratch, beta, y, **kw):
+        return self.parent._apply(alpha, self._flip(P), x, scratch, beta, y, **kw)
 
 
 class Composition(LinearMapping):
@@ -194,15 +194,17 @@ class Composition(LinearMapping):
             y = f._vcreate(P, y)
         return y
 
-    def _separable(self, P, x):
+    @staticmethod
+    def _sep_group(factors, N):
+        """``factors`` (any order) are table-backed interpolators along distinct dimensions of an N-d array, all
+        direct or all adjoint -> (tabs, flipped), else None."""
         from .tabulated import TabulatedInterpolator
         from .sparse import SparseUnidimensionalInterpolator
-        N = len(ar.shape_of(x))
-        if N < 2 or N > 3 or len(self.factors) < 2:
+        if N < 2 or N > 3 or len(factors) < 2:
             return None
         tabs = [None] * N
         flips = set()
-        for f in self.factors:
+        for f in factors:
             g, flip = (f.parent, True) if isinstance(f, AdjointMapping) else (f, False)
             if not isinstance(g, (TabulatedInterpolator, SparseUnidimensionalInterpolator)):
                 return None
@@ -213,25 +215,74 @@ class Composition(LinearMapping):
             flips.add(flip)
         if len(flips) != 1:
             return None
-        adjoint = (P is Adjoint) != flips.pop()
-        return tabs, adjoint
+        return tabs, flips.pop()
+
+    def _separable(self, P, x):
+        g = self._sep_group(self.factors, len(ar.shape_of(x)))
+        if g is None:
+            return None
+        tabs, flip = g
+        return tabs, (P is Adjoint) != flip
+
+    def _runs(self, P, N):
+        """The factors in application order, cut into maximal runs that one fused separable apply can take
+        (e.g. ``H'*H`` with ``H = A1*A2`` is two runs: H, then H')."""
+        runs, cur = [], []
+        for f in self._order(P):
+            if self._is_tab(f, N):
+                if cur and self._sep_group(cur + [f], N) is not None:
+                    cur.append(f)
+                else:
+                    if cur:
+                        runs.append(cur)
+                    cur = [f]
+            else:
+                if cur:
+                    runs.append(cur)
+                    cur = []
+                runs.append([f])
+        if cur:
+            runs.append(cur)
+        return runs
+
+    @staticmethod
+    def _is_tab(f, N):
+        from .tabulated import TabulatedInterpolator
+        from .sparse import SparseUnidimensionalInterpolator
+        g = f.parent if isinstance(f, AdjointMapping) else f
+        return isinstance(g, (TabulatedInterpolator, SparseUnidimensionalInterpolator)) and isinstance(g.d, int) \
+            and 1 <= g.d <= N
 
     def _apply(self, alpha, P, x, scratch, beta, y):
-        sep = self._separable(P, x) if _is_array(x) else None
+        from .separable import sep_apply_tables
+        # (complex data: each factor handles Complex{T} as T with a leading dimension of 2, src/tabulated.jl:196;
+        # the fused kernels work on real arrays of the table's type)
+        real = _is_array(x) and not isinstance(x, (list, tuple)) and ar.np_dtype_of(x).kind != "c"
+        sep = self._separable(P, x) if real else None
         if sep is not None:
-            from .separable import sep_apply_tables
             tabs, adjoint = sep
             return sep_apply_tables(adjoint, tabs, alpha, x, beta, y, owner=self)
-        order = self._order(P)
+        N = len(ar.shape_of(x)) if _is_array(x) and not isinstance(x, (list, tuple)) else 0
+        runs = self._runs(P, N) if real and 2 <= N <= 3 else [[f] for f in self._order(P)]
         cur = x
-        for k, f in enumerate(order):
-            last = k == len(order) - 1
-            if last:
-                f._apply(alpha, P, cur, scratch, beta, y)
+        for k, run in enumerate(runs):
+            last = k == len(runs) - 1
+            a, b_ = (alpha, beta) if last else (1, 0)
+            if len(run) >= 2:
+                tabs, flip = self._sep_group(run, N)
+                adjoint = (P is Adjoint) != flip
+                if last:
+                    out = y
+                else:
+                    out = cur
+                    for f in run:
+                        out = f._vcreate(P, out)
+                sep_apply_tables(adjoint, tabs, a, cur, b_, out, owner=self)
             else:
-                tmp = f._vcreate(P, cur)
-                f._apply(1, P, cur, scratch, 0, tmp)
-                cur = tmp
+                f = run[0]
+                out = y if last else f._vcreate(P, cur)
+                f._apply(a, P, cur, scratch, b_, out)
+            cur = out
         return y
 
 
@@ -349,7 +400,12 @@ apply_ = apply_b
 
 
 def vdot(x, y) -> float:
-    """LazyAlgebra ``vdot`` for real arrays (accumulated in Float64 on the host; diagnostics only)."""
+    """LazyAlgebra ``vdot`` for real arrays, accumulated in Float64: on the device (``li_vdot``, fixed reduction
+    order) when both arguments are device arrays, else on the host."""
+    if ar.is_device(x) and ar.is_device(y) and ar.np_dtype_of(x) == ar.np_dtype_of(y) and ar.np_dtype_of(x).kind == "f" \
+            and ar.is_colmajor(x) and ar.is_colmajor(y):
+        from .solvers import vdot_device
+        return vdot_device(x, y)
     return float(np.vdot(ar.to_host(x).astype(np.float64).ravel(order="F"),
                          ar.to_host(y).astype(np.float64).ravel(order="F")))
 

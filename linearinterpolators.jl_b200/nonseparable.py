@@ -146,6 +146,8 @@ class TwoDimensionalTransformInterpolator(LinearMapping):
     def _apply(self, alpha, P, x, scratch, beta, y):
         x = ar.to_colmajor(x, self.eltype)
         xin, yout = (self.cols, self.rows) if P is Direct else (self.rows, self.cols)
-        assert ar.shape_of(x) == xin, "size(x) == A.cols" if P is Direct else "size(x) == A.rows"   # :85,98
-        assert ar.shape_of(y) == yout, "size(y) == A.rows" if P is Direct else "size(y) == A.cols"  # :86,99
+        if ar.shape_of(x) != xin:      # @assert of src/nonseparable.jl:85,98 (kept under `python -O`)
+            raise AssertionError("size(x) == A.cols" if P is Direct else "size(x) == A.rows")
+        if ar.shape_of(y) != yout:     # :86,99
+            raise AssertionError("size(y) == A.rows" if P is Direct else "size(y) == A.cols")
         return affine_apply(alpha, P, self.ker1, self.ker2, self.R, x, beta, y)

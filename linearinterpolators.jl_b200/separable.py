@@ -117,10 +117,12 @@ def sep2d_otf_apply(alpha, P, ker1, x1, ker2, x2, src, beta, dst):
     if len(ss) != 2 or len(ds) != 2:
         raise TypeError("source and destination must be 2-dimensional")
     if adjoint:
-        assert ss == (n1, n2), "size(src) == (length(x1), length(x2))"          # :143
+        if ss != (n1, n2):                                                      # @assert, :143
+            raise AssertionError("size(src) == (length(x1), length(x2))")
         m1, m2 = ds
     else:
-        assert ds == (n1, n2), "size(dst) == (length(x1), length(x2))"          # :78
+        if ds != (n1, n2):                                                      # @assert, :78
+            raise AssertionError("size(dst) == (length(x1), length(x2))")
         m1, m2 = ss
     check_dst(dst, ds, T)
     check_same_kind(src, dst)

@@ -46,12 +46,14 @@ def otf1d_apply(alpha, P, ker, x, src, beta, dst, variant=_lib.VARIANT_AUTO):
     src = ar.to_colmajor(src, T)
     xshape = ar.shape_of(x) if hasattr(x, "shape") else np.asarray(x).shape
     if adjoint:
-        assert ar.shape_of(src) == tuple(xshape), "size(src) == size(x)"        # :197
+        if ar.shape_of(src) != tuple(xshape):                                   # @assert, :197
+            raise AssertionError("size(src) == size(x)")
         if len(ar.shape_of(dst)) != 1:
             raise TypeError("destination of the adjoint must be a vector")
         length = ar.shape_of(dst)[0]
     else:
-        assert ar.shape_of(dst) == tuple(xshape), "size(dst) == size(x)"        # :105
+        if ar.shape_of(dst) != tuple(xshape):                                   # @assert, :105
+            raise AssertionError("size(dst) == size(x)")
         if len(ar.shape_of(src)) != 1:
             raise TypeError("source must be a vector")
         length = ar.shape_of(src)[0]

@@ -23,7 +23,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in li_b200.h but not exported"
     assert set(names) == set(li_b200._lib.EXPORTED), "python binding and header disagree"
-    assert li_b200.version() == 100
+    assert li_b200.version() == 200
 
 
 def test_product_never_imports_the_oracle():

@@ -60,3 +60,27 @@ def hostile_positions(ncols, T, rng, n=257):
             float(np.nextafter(T(0), T(-1))), float(np.nextafter(T(1), T(0)))]
     extra = rng.uniform(-4, ncols + 5, n - len(base))
     return np.concatenate([np.array(base), extra]).astype(T)
+
+
+def assert_within_bound(a, b, bound, dtype, what=""):
+    """Strict per-element parity check of SURVEY.md Appendix F: |a_i - b_i| <= rtol * sum_s |w_s * src_{j_s}|, the
+    natural forward-error scale of a banded dot product (`bound` = the same operator applied with |w| to |src|).
+    rtol = 1e-6 (Float32) / 1e-12 (Float64), no extra factor."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    bound = np.asarray(bound, dtype=np.float64)
+    assert a.shape == b.shape == bound.shape, (a.shape, b.shape, bound.shape)
+    tol = RTOL[np.dtype(dtype)] * bound + np.finfo(np.float64).tiny
+    bad = np.abs(a - b) > tol
+    if bad.any():
+        k = np.unravel_index(np.argmax(np.abs(a - b) / tol), a.shape)
+        raise AssertionError(f"{what}: {int(bad.sum())} elements out of bound; worst at {k}: |{a[k]} - {b[k]}| = "
+                             f"{abs(a[k] - b[k]):.3e} > {tol[k]:.3e}")
+    return float(np.max(np.abs(a - b) / tol)) if a.size else 0.0
+
+
+def sep2d_oracle(J1, W1, m1, J2, W2, m2, x, adjoint):
+    """A1*A2 (or its adjoint) with the reference's per-dimension loops and order (A2 first / A1' first)."""
+    if not adjoint:
+        return O.tab_direct(J1, W1, m1, 1, O.tab_direct(J2, W2, m2, 2, x))
+    return O.tab_adjoint(J2, W2, m2, 2, O.tab_adjoint(J1, W1, m1, 1, x))
