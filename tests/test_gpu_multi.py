@@ -56,6 +56,9 @@ CASES = [
     ("CatmullRomSpline", 4, O.SAFEFLAT, 520, 96, 520, 96, 6, 1.0, 3.0),    # several strips, a single chunk
     ("LinearSpline", 2, O.FLAT, 260, 300, 260, 300, 4, 1.0, 0.7),
     ("QuadraticSpline", 3, O.FLAT, 128, 200, 128, 200, 4, 1.0, 2.2),
+    ("LanczosKernel", 6, O.SAFEFLAT, 301, 283, 300, 280, 5, 1.0, 8.0),     # odd model width: the last column pair is half empty
+    ("CatmullRomSpline", 4, O.FLAT, 200, 190, 300, 284, 4, 1.5, 2.0),      # irregular rate: generic row schedule everywhere
+    ("LanczosKernel", 4, O.FLAT, 1100, 64, 1100, 64, 3, 1.0, 6.0),         # three strips, wide tap lists at the edges
 ]
 
 
@@ -68,6 +71,8 @@ def test_multi_frame_accumulate_matches_oracle(li, case, T):
     model0 = np.asfortranarray(rng.standard_normal((m1, m2)).astype(T))
     dys = [li.to_device(y) for y in ys]
     tl = [(a.table, b.table) for a, b in tabs]
+    # (the first call builds the per-table adjoint metadata and the plan of the batch: several one-off launches)
+    li.adjoint_accumulate(tl, dys, li.to_device(model0), alpha=1, beta=0)
     for alpha, beta in ((1, 0), (1, 1), (-0.5, 2.0)):
         ref, bound = _oracle_sum(otabs, ys, m1, m2, alpha, beta, model0, T)
         model = li.to_device(model0)
