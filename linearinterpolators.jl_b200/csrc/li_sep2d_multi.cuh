@@ -190,13 +190,6 @@ sep2d_adj_multi_kernel(const MultiArgs<T> a)
             const Pre p = nx;
             if (f + 1 < f1) nx = fetch(f + 1);                    // (in flight while this frame's weights are staged)
             const int i2lo = p.g.x, NR = p.g.y;
-            {   // pull the src rows of this frame that feed the tile into L2: the ring's copies then see L2 latency
-                const int cv1 = min(P1, p.n1 - p.g.z);
-                for (int r = lane; r < NR; r += 32)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.src + (int64_t)(i2lo + r) * p.n1 + p.g.z),
-                                 "r"((uint32_t)(cv1 * sizeof(T)))
-                                 : "memory");
-            }
             mbar_wait(&mempty[ms], mph ^ 1u);                     // everybody is done with the frame NM frames back
             T *w2 = sW2 + (size_t)ms * a.NRMAX * W2P;
             for (int k = lane; k < NR * S2; k += 32) w2[(k / S2) * W2P + k % S2] = a.alpha * p.W2f[(int64_t)i2lo * S2 + k];
