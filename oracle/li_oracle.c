@@ -181,6 +181,12 @@ float lio_sin_f32(float x)
     }
 }
 
+/* Error-scale helpers for the tests (tests/util.py): the on-the-fly and affine loops can be run with every weight
+ * replaced by its magnitude (mode 1: "the same operator applied with |w| to |src|", the per-element error bound of
+ * SURVEY.md Appendix F) or by 1 where it is non-zero (mode 2: the number of products summed into an element). */
+int lio_weight_mode_ = 0;
+void lio_set_weight_mode(int mode) { lio_weight_mode_ = mode; }
+
 int lio_max_threads(void)
 {
 #ifdef _OPENMP

@@ -99,6 +99,8 @@ LIO_DECLARE(float, f32)
 LIO_DECLARE(double, f64)
 
 int lio_max_threads(void);
+void lio_set_weight_mode(int mode);   /* test helper: 0 = weights as they are, 1 = |w|, 2 = (w != 0) */
+extern int lio_weight_mode_;
 
 #ifdef __cplusplus
 }

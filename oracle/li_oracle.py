@@ -267,5 +267,21 @@ def affine2d(adjoint: bool, k1, k2, R, rows, cols, src, dtype, alpha=1, beta=0, 
     return dst
 
 
+class weight_mode:
+    """Context manager for the error-scale helpers of the tests: inside it, the affine loops use |w| (mode 1) or
+    (w != 0) (mode 2) in place of every weight."""
+
+    def __init__(self, mode: int):
+        self.mode = int(mode)
+
+    def __enter__(self):
+        lib().lio_set_weight_mode(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        lib().lio_set_weight_mode(0)
+        return False
+
+
 def max_threads() -> int:
     return int(lib().lio_max_threads())

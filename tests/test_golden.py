@@ -95,3 +95,48 @@ def test_cuda_reproduces_golden_sep2d_and_affine(gold, T):
     outa = np.zeros((31, 29), dtype=T, order="F")
     li.apply_b(1, li.Adjoint, cr, cr, R, np.asfortranarray(gold[f"aff_y_{tn}"]), 0, outa)
     assert_close(outa, gold[f"aff_adj_{tn}"], T, factor=16)
+
+
+# ------------------------------------------------------------------------------------------------
+# Vectors of the REAL reference, when somebody has produced them (baseline/julia/dump_goldens.jl; needs Julia, which the
+# build image does not have): baseline/_ref/goldens/<tag>.{J,W,dir,adj}.bin.  With them the oracle -- and through it the
+# CUDA tables -- are pinned to Julia bit for bit instead of "parity unpinned" (SURVEY.md section 8c).
+JULIA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "goldens")
+have_julia = os.path.exists(os.path.join(JULIA, "cases.tsv"))
+
+
+def _julia_case(tag, T, S, nrows, ncols, nb):
+    rd = lambda part, dt, shape: np.fromfile(os.path.join(JULIA, f"{tag}.{part}.bin"), dtype=dt).reshape(shape, order="F")
+    return rd("J", np.int64, (S, nrows)), rd("W", T, (S, nrows)), rd("dir", T, (nrows, nb)), rd("adj", T, (ncols, nb))
+
+
+@pytest.mark.skipif(not have_julia, reason="no Julia goldens (baseline/julia/dump_goldens.jl has not been run)")
+@pytest.mark.parametrize("ki,cname,cond,T", CASES, ids=CASE_IDS)
+def test_oracle_matches_julia_goldens(gold, ki, cname, cond, T):
+    import li_oracle as O
+    tag = f"{ki:02d}_{cname}_{np.dtype(T).name}"
+    if os.path.exists(os.path.join(JULIA, f"{tag}.error.txt")):
+        pytest.skip("the reference throws on these positions")
+    S = KERNELS[ki][2]
+    Jj, Wj, dj, aj = _julia_case(tag, T, S, gold[f"x_{tag}"].size, NCOLS, gold[f"src_{tag}"].shape[1])
+    J, W = O.maketable(oracle_kernel(KERNELS[ki], cond), gold[f"x_{tag}"], NCOLS, T)
+    assert np.array_equal(J, Jj), "index table differs from Julia"
+    assert _bits_equal(W, Wj), "weights differ from Julia (InterpolationKernels formula or operation order)"
+    assert_close(O.tab_direct(J, W, NCOLS, 1, np.asfortranarray(gold[f"src_{tag}"])), dj, T, factor=4)
+    assert_close(O.tab_adjoint(J, W, NCOLS, 1, np.asfortranarray(gold[f"y_{tag}"])), aj, T, factor=16)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_julia, reason="no Julia goldens (baseline/julia/dump_goldens.jl has not been run)")
+@pytest.mark.parametrize("ki,cname,cond,T", CASES, ids=CASE_IDS)
+def test_cuda_matches_julia_goldens(gold, ki, cname, cond, T):
+    import li_b200 as li
+    tag = f"{ki:02d}_{cname}_{np.dtype(T).name}"
+    if os.path.exists(os.path.join(JULIA, f"{tag}.error.txt")):
+        pytest.skip("the reference throws on these positions")
+    S = KERNELS[ki][2]
+    Jj, Wj, dj, aj = _julia_case(tag, T, S, gold[f"x_{tag}"].size, NCOLS, gold[f"src_{tag}"].shape[1])
+    A = li.TabulatedInterpolator(T, 1, product_kernel(li, KERNELS[ki], cond, T), gold[f"x_{tag}"], NCOLS)
+    assert np.array_equal(A.J, Jj) and _bits_equal(np.asarray(A.W), Wj)
+    assert_close(A * np.asfortranarray(gold[f"src_{tag}"]), dj, T, factor=4)
+    assert_close(A.adj * np.asfortranarray(gold[f"y_{tag}"]), aj, T, factor=16)

@@ -14,6 +14,14 @@ def kernels(T):
     return [li.LinearSpline(T), li.CatmullRomSpline(T), li.CubicSpline(T), li.LanczosKernel(T, 4), li.LanczosKernel(T, 6), li.QuadraticSpline(T),
             li.SafeFlat(li.LanczosKernel(T, 4)), li.SafeFlat(li.CatmullRomSpline(T)), li.SafeFlat(li.LanczosKernel(T, 6))]
 
+def _ratio(got, want, T):
+    """worst |got - want| / tolerance over the elements: tolerance = the stated rtol (1e-6 / 1e-12) times the element's
+    own error scale sum |w * src| (times terms / 32 where more than 32 products are summed), see tests/util.py"""
+    from util import RTOL, TERMS0
+    tol = RTOL[np.dtype(T)] * want.bound * np.maximum(1.0, want.terms / TERMS0) + np.finfo(np.float64).tiny
+    return float(np.max(np.abs(got.astype(np.float64) - np.asarray(want, dtype=np.float64)) / tol))
+
+
 def positions(style, m, n, rng):
     if style == 0: return np.linspace(1.0, float(m), n)
     if style == 1: return np.linspace(-rng.uniform(0, 9), m + rng.uniform(0, 9), n)
@@ -24,6 +32,7 @@ def positions(style, m, n, rng):
 def main(ncases, seed):
     global li
     import li_b200 as li
+    from util import RO as O
     rng = np.random.default_rng(seed)
     worst = 0.0
     for case in range(ncases):
@@ -41,24 +50,22 @@ def main(ncases, seed):
         src = li.to_device(np.asfortranarray(rng.standard_normal((m1, m2, nb)).astype(T)))
         y = li.to_device(np.asfortranarray(rng.standard_normal((n1, n2, nb)).astype(T)))
         alpha, beta = (1.0, 0.0) if rng.random() < 0.5 else (float(rng.uniform(-2, 2)), float(rng.choice([0.0, 1.0, -0.5])))
-        res = {}
-        for mode in ("fused", "passes"):
-            if mode == "passes": os.environ["LI_B200_NO_FUSED"] = "1"
-            else: os.environ.pop("LI_B200_NO_FUSED", None)
-            out = li.to_device(np.asfortranarray(np.ones((n1, n2, nb), dtype=T)))
-            back = li.to_device(np.asfortranarray(np.ones((m1, m2, nb), dtype=T)))
-            li.sep_apply_tables(False, [A1.table, A2.table], alpha, src, beta, out, nbatch_dims=1)
-            li.sep_apply_tables(True, [A1.table, A2.table], alpha, y, beta, back, nbatch_dims=1)
-            res[mode] = (li.to_host(out).astype(np.float64), li.to_host(back).astype(np.float64))
-        os.environ.pop("LI_B200_NO_FUSED", None)
-        tol = (2e-5 if T == np.float32 else 1e-11)
-        for idx, name in ((0, "forward"), (1, "adjoint")):
-            a, b = res["fused"][idx], res["passes"][idx]
-            scale = max(np.max(np.abs(b)), 1e-30)
-            err = np.max(np.abs(a - b)) / scale
-            worst = max(worst, err / tol)
-            if not np.isfinite(err) or err > tol:
-                print(f"MISMATCH case {case} {name}: err {err:.3e} T={np.dtype(T).name} k1={type(k1).__name__}/{k1.S} k2={type(k2).__name__}/{k2.S} "
+        d0 = np.asfortranarray(rng.standard_normal((n1, n2, nb)).astype(T))
+        c0 = np.asfortranarray(rng.standard_normal((m1, m2, nb)).astype(T))
+        out, back = li.to_device(d0), li.to_device(c0)
+        li.sep_apply_tables(False, [A1.table, A2.table], alpha, src, beta, out, nbatch_dims=1)
+        li.sep_apply_tables(True, [A1.table, A2.table], alpha, y, beta, back, nbatch_dims=1)
+        # the oracle on the product's own tables (bit-equal to the oracle's, tests/test_gpu_parity.py): the reference's
+        # two passes (A2 then A1; A1' then A2'), alpha and beta in the last one
+        J1, W1, J2, W2 = A1.J, A1.W, A2.J, A2.W
+        hs, hy = li.to_host(src), li.to_host(y)
+        ref = O.tab_direct(J1, W1, m1, 1, O.tab_direct(J2, W2, m2, 2, hs), alpha, beta, d0.copy(order="F"))
+        refa = O.tab_adjoint(J2, W2, m2, 2, O.tab_adjoint(J1, W1, m1, 1, hy), alpha, beta, c0.copy(order="F"))
+        for got, want, name in ((li.to_host(out), ref, "forward"), (li.to_host(back), refa, "adjoint")):
+            err = _ratio(got, want, T)
+            worst = max(worst, err)
+            if not np.isfinite(err) or err > 1:
+                print(f"MISMATCH case {case} {name}: err / tol {err:.3e} T={np.dtype(T).name} k1={type(k1).__name__}/{k1.S} k2={type(k2).__name__}/{k2.S} "
                       f"m=({m1},{m2}) n=({n1},{n2}) nb={nb} styles=({s1},{s2}) alpha={alpha} beta={beta}", flush=True)
                 return 1
     print(f"{ncases} cases ok, worst err / tol = {worst:.3f}")
@@ -67,7 +74,10 @@ def main(ncases, seed):
 
 
 @pytest.mark.parametrize("seed", [11, 12, 13])
-def test_fused_kernels_match_per_dimension_passes(seed):
+def test_fused_kernels_match_oracle(seed):
+    """Random kernels, boundary conditions, sizes, rates (up-, down-, same-rate sampling, unsorted positions), batches,
+    alpha / beta, both element types: the fused 2-D dispatch (streaming, tile and fallback kernels) against the CPU
+    oracle's two passes, per element at the stated tolerance."""
     assert main(60, seed) == 0
 
 
@@ -111,7 +121,7 @@ def test_affine_tiled_forward_is_bit_identical_to_per_pixel_kernel(seed):
 
 def tab_main(ncases, seed):
     import li_b200 as li
-    import li_oracle as O
+    from util import RO as O
     from util import KERNELS, CONDITIONS, oracle_kernel, product_kernel
     rng = np.random.default_rng(seed)
     worst = 0.0
@@ -144,13 +154,11 @@ def tab_main(ncases, seed):
         refa = O.tab_adjoint(J, W, ncols, d, y, alpha, beta, c0.copy(order="F"))
         dc = li.to_device(c0)
         li.apply_b(alpha, li.Adjoint, A, li.to_device(y), False, beta, dc)
-        tol = 4e-6 if T == np.float32 else 1e-11
         for got, want, name in ((li.to_host(dd), ref, "direct"), (li.to_host(dc), refa, "adjoint")):
-            scale = float(np.max(np.abs(want))) + 1.0
-            err = float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64)))) / scale
-            worst = max(worst, err / tol)
-            if not np.isfinite(err) or err > tol:
-                print(f"MISMATCH case {case} {name}: err {err:.3e} T={np.dtype(T).name} {entry[0]} {cname} shape={shape} d={d} nrows={nrows} style={style} alpha={alpha} beta={beta}", flush=True)
+            err = _ratio(got, want, T)
+            worst = max(worst, err)
+            if not np.isfinite(err) or err > 1:
+                print(f"MISMATCH case {case} {name}: err / tol {err:.3e} T={np.dtype(T).name} {entry[0]} {cname} shape={shape} d={d} nrows={nrows} style={style} alpha={alpha} beta={beta}", flush=True)
                 return 1
     print(f"{ncases} cases ok, worst err / tol = {worst:.3f}")
     return 0
@@ -167,7 +175,7 @@ def test_per_dimension_applies_match_oracle(seed):
 
 def affine_main(ncases, seed):
     import li_b200 as li
-    import li_oracle as O
+    from util import RO as O
     from util import KERNELS, CONDITIONS, oracle_kernel, product_kernel
     rng = np.random.default_rng(seed)
     worst = 0.0
@@ -195,14 +203,10 @@ def affine_main(ncases, seed):
         li.affine_apply(alpha, li.Direct, k1, k2, R, li.to_device(x), beta, dd)
         li.affine_apply(alpha, li.Adjoint, k1, k2, R, li.to_device(y), beta, dc)
         for got, want, name in ((li.to_host(dd), ref, "direct"), (li.to_host(dc), refa, "adjoint")):
-            # 1e-6 / 1e-12 relative times the factors of tests/test_gpu_parity.py::test_affine (8 direct, 64 adjoint:
-            # border elements of the adjoint accumulate thousands of clamped contributions, in a different order)
-            tol = (1e-6 if T == np.float32 else 1e-12) * (8 if name == "direct" else 64)
-            scale = float(np.max(np.abs(want))) + 1.0
-            err = float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64)))) / scale
-            worst = max(worst, err / tol)
-            if not np.isfinite(err) or err > tol:
-                print(f"MISMATCH case {case} {name}: err {err:.3e} T={np.dtype(T).name} {e1[0]}/{c1n} {e2[0]}/{c2n} rows={rows} cols={cols} alpha={alpha} beta={beta} R={Rc}", flush=True)
+            err = _ratio(got, want, T)
+            worst = max(worst, err)
+            if not np.isfinite(err) or err > 1:
+                print(f"MISMATCH case {case} {name}: err / tol {err:.3e} T={np.dtype(T).name} {e1[0]}/{c1n} {e2[0]}/{c2n} rows={rows} cols={cols} alpha={alpha} beta={beta} R={Rc}", flush=True)
                 return 1
     print(f"{ncases} cases ok, worst err / tol = {worst:.3f}")
     return 0

@@ -4,7 +4,7 @@ the CPU oracle on identical inputs.  Tables must match bit for bit; interpolated
 import numpy as np
 import pytest
 
-import li_oracle as O
+from util import RO as O   # the oracle, with per-element error bounds attached to its results
 from util import (CONDITIONS, DTYPES, KERNEL_IDS, KERNELS, assert_close, hostile_positions, oracle_kernel,
                   product_kernel)
 
