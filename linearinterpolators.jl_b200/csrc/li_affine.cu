@@ -14,6 +14,15 @@ extern template int affine_T<float>(int, const li_kernel_desc *, const li_kernel
                                     int64_t, int64_t, double, const void *, double, void *, int *, bool, cudaStream_t);
 extern template int affine_T<double>(int, const li_kernel_desc *, const li_kernel_desc *, const double[6], int64_t, int64_t, int64_t,
                                      int64_t, int64_t, double, const void *, double, void *, int *, bool, cudaStream_t);
+// gather-form adjoint (li_affine_gather.cuh): *done stays false when it declines the operator
+template <typename T>
+int affine_adjoint_gather(const li_kernel_desc *ker1, const li_kernel_desc *ker2, const double R[6], int64_t n1, int64_t n2, int64_t m1,
+                          int64_t m2, int64_t nbatch, double alpha, const void *src, double beta, void *dst, int *err, cudaStream_t st,
+                          bool *done);
+extern template int affine_adjoint_gather<float>(const li_kernel_desc *, const li_kernel_desc *, const double[6], int64_t, int64_t, int64_t,
+                                                 int64_t, int64_t, double, const void *, double, void *, int *, cudaStream_t, bool *);
+extern template int affine_adjoint_gather<double>(const li_kernel_desc *, const li_kernel_desc *, const double[6], int64_t, int64_t, int64_t,
+                                                  int64_t, int64_t, double, const void *, double, void *, int *, cudaStream_t, bool *);
 }  // namespace li
 
 extern "C" int li_affine2d_apply(int adjoint, const li_kernel_desc *ker1, const li_kernel_desc *ker2,
@@ -22,8 +31,9 @@ extern "C" int li_affine2d_apply(int adjoint, const li_kernel_desc *ker1, const 
                                  void *stream)
 {
     // direct: LI_VARIANT_AUTO = tiled kernel (source boxes staged in shared memory), LI_VARIANT_ATOMIC = one thread
-    // per pixel straight on global memory (the first implementation, kept for comparison); the adjoint is the
-    // atomic scatter in both cases
+    // per pixel straight on global memory (the first implementation, kept for comparison).  Adjoint: LI_VARIANT_AUTO /
+    // LI_VARIANT_GATHER = the deterministic gather form (li_affine_gather.cuh) when it takes the operator, else --
+    // and with LI_VARIANT_ATOMIC -- the atomic scatter
     const bool tiled = !adjoint && variant != LI_VARIANT_ATOMIC && !li::opt(li::OPT_AFFINE_PLAIN);
     LI_REQUIRE(ker1 && ker2 && R && dst_dev, LI_ERR_ARG, "null argument");
     LI_REQUIRE(ker1->dtype == ker2->dtype, LI_ERR_ARG, "kernels must share one floating-point type");
@@ -37,15 +47,25 @@ extern "C" int li_affine2d_apply(int adjoint, const li_kernel_desc *ker1, const 
     if (alpha == 0.0) return li::vscale_impl(dtype, dst_dev, nout, beta, st);  // :169-172
     LI_REQUIRE(src_dev, LI_ERR_ARG, "null source");
     if (n1 == 0 || n2 == 0) return li::vscale_impl(dtype, dst_dev, nout, beta, st);
-    if (adjoint) {
-        int rc = li::vscale_impl(dtype, dst_dev, nout, beta, st);  // :236
-        if (rc != LI_OK) return rc;
-    }
     static thread_local std::map<int, int *> d_errs;   // per device
     int *&d_err = d_errs[li::current_device()];
     if (!d_err) LI_CUDA(cudaMalloc(&d_err, sizeof(int)));
     LI_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
-    int rc = dtype == LI_F32 ? li::affine_T<float>(adjoint, ker1, ker2, R, n1, n2, m1, m2, nbatch, alpha, src_dev,
+    int rc = LI_OK;
+    bool gathered = false;
+    if (adjoint && variant != LI_VARIANT_ATOMIC && !li::opt(li::OPT_AFFINE_PLAIN)) {
+        rc = dtype == LI_F32 ? li::affine_adjoint_gather<float>(ker1, ker2, R, n1, n2, m1, m2, nbatch, alpha, src_dev, beta, dst_dev,
+                                                                d_err, st, &gathered)
+                             : li::affine_adjoint_gather<double>(ker1, ker2, R, n1, n2, m1, m2, nbatch, alpha, src_dev, beta, dst_dev,
+                                                                 d_err, st, &gathered);
+        if (rc != LI_OK) return rc;
+    }
+    if (adjoint && !gathered) {
+        rc = li::vscale_impl(dtype, dst_dev, nout, beta, st);  // :236
+        if (rc != LI_OK) return rc;
+    }
+    if (!gathered)
+    rc = dtype == LI_F32 ? li::affine_T<float>(adjoint, ker1, ker2, R, n1, n2, m1, m2, nbatch, alpha, src_dev,
                                                    beta, dst_dev, d_err, tiled, st)
                              : li::affine_T<double>(adjoint, ker1, ker2, R, n1, n2, m1, m2, nbatch, alpha, src_dev,
                                                     beta, dst_dev, d_err, tiled, st);
@@ -53,6 +73,10 @@ extern "C" int li_affine2d_apply(int adjoint, const li_kernel_desc *ker1, const 
     int h_err = 0;
     LI_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     LI_CUDA(cudaStreamSynchronize(st));
+    if (h_err >= 2) {
+        li::set_error("internal: the gather-form affine adjoint ran out of room (%s)", h_err == 3 ? "candidate box" : "cell overflow list");
+        return LI_ERR_UNSUPPORTED;
+    }
     if (h_err) {
         li::set_error("InexactError: trunc(Int64, f) for a NaN or out-of-range coordinate");
         return LI_ERR_INEXACT;
