@@ -80,10 +80,17 @@ def cfg3(li, torch, nb):
     src = li.device_empty((n, n, nb), T)
     src.normal_()
     dst = li.device_empty((n, n, nb), T)
-    for P, name in ((li.Direct, "forward"), (li.Adjoint, "adjoint (atomic)")):
-        fn = lambda: li.affine_apply(1, P, ker, ker, R, src, 0, dst, nbatch_dims=1)
+    for P, name, variant in ((li.Direct, "forward", li.VARIANT_AUTO), (li.Adjoint, "adjoint (gather form, deterministic)", li.VARIANT_AUTO),
+                             (li.Adjoint, "adjoint (atomic variant)", li.VARIANT_ATOMIC)):
+        fn = lambda: li.affine_apply(1, P, ker, ker, R, src, 0, dst, variant=variant, nbatch_dims=1)
         t = timeit(fn, 5, warm=2)
         report(f"#3 affine rotation CatmullRom F32 8192^2 x {nb} {name}", n * n * nb, 2 * n * n * 4 * nb, *t)
+    # one image at a time (the reference's own call shape: the type is strictly 2-D)
+    one_s, one_d = src[:, :, 0], dst[:, :, 0]
+    for variant, name in ((li.VARIANT_AUTO, "gather form"), (li.VARIANT_ATOMIC, "atomic variant")):
+        fn = lambda: li.affine_apply(1, li.Adjoint, ker, ker, R, one_s, 0, one_d, variant=variant)
+        t = timeit(fn, 5, warm=2)
+        report(f"#3 affine rotation, adjoint of a single 8192^2 image, {name}", n * n, 2 * n * n * 4, *t)
 
 
 def cfg4(li, torch):

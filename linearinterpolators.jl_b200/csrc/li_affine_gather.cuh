@@ -41,12 +41,14 @@ constexpr int AG_KC = 2;         // pixels a cell holds in the per-element regis
 constexpr int AG_NOVF = 16;      // overflow entries per tile (cells that received a third pixel: position rounding)
 constexpr int AG_NSTG = 4;       // boxes (images) in flight per CTA
 constexpr int AG_ITEM = 2048;    // border entries per work item
+constexpr int AG_SLOTB = 12288;  // bytes per ring slot (128 bytes of zero pad + the staged box)
 
 struct AGParams {
     double ixx, ixy, iyx, iyy;   // inverse of the linear part of R (positions -> pixel indices)
     int BW, BH;                  // candidate box of a tile (src pixels), upper bounds
     int PB, HB;                  // staged box (TMA): PB >= BW + alignment slack, HB >= BH; PB = row pitch
     int bulk;                    // boxes arrive by tensor-map TMA (else plain loads)
+    int ring_off;                // byte offset of the ring of boxes in dynamic shared memory
 };
 
 template <typename T, int S1, int S2, int TD2>
@@ -60,10 +62,10 @@ affine_adj_gather_kernel(AffineArgs<T> a, AGParams g, const T *__restrict__ src,
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // phase 1: [cand weights][cells]   phase 2: [zero pad | boxes ...] over the same bytes
     const int NCAND = (g.BW + AL - 1) * g.BH;                   // (a TMA box starts at an aligned column: up to AL-1 more)
-    T *sw1 = reinterpret_cast<T *>(smem_raw);                   // [NCAND][S1]
-    T *sw2 = sw1 + (size_t)NCAND * S1;                          // [NCAND][S2]
-    int *ccnt = reinterpret_cast<int *>(sw2 + (size_t)NCAND * S2);   // [CW*CH]
-    unsigned short *cpix = reinterpret_cast<unsigned short *>(ccnt + CW * CH);   // [CW*CH][KC]
+    T *sw1 = reinterpret_cast<T *>(smem_raw);                   // [NCAND + 1][S1] (the last one: the sentinel, zeros)
+    T *sw2 = sw1 + (size_t)(NCAND + 1) * S1;                    // [NCAND + 1][S2]
+    int *ccnt = reinterpret_cast<int *>(sw2 + (size_t)(NCAND + 1) * S2);   // [CW*CH]
+    ushort2 *cpix = reinterpret_cast<ushort2 *>(ccnt + CW * CH);   // [CW*CH][KC] {candidate (index of its weights), offset in the staged box}
     struct Ovf {                                                // a pixel that found its cell full
         int u1, u2, off;
         T w1[S1], w2[S2];
@@ -101,113 +103,29 @@ affine_adj_gather_kernel(AffineArgs<T> a, AGParams g, const T *__restrict__ src,
         for (int k = 0; k < AG_NSTG; ++k) mbar_init(&bar[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // Empty cell entries point at a sentinel candidate (index NCAND: zero weights) and at offset 0 of the ring slot, a
+    // zero word in front of the box (box offsets are stored + PADN): the list building below needs no branches.
+    constexpr int PADN = 128 / (int)sizeof(T);
     for (int k = tid; k < CW * CH; k += NT) ccnt[k] = 0;
+    for (int k = tid; k < CW * CH * KC; k += NT) cpix[k] = make_ushort2((unsigned short)NCAND, 0);
+    for (int k = tid; k < S1 + S2; k += NT) (k < S1 ? sw1[NCAND * S1 + k] : sw2[NCAND * S2 + (k - S1)]) = (T)0;
     __syncthreads();
     const int I1a = sbox[0], I2a = sbox[1], nb1 = sbox[2], nb2 = sbox[3];
     const int P = g.bulk ? g.PB : g.BW;          // row pitch of the staged box
+    const unsigned inv1 = nb1 > 1 ? (unsigned)((1ull << 32) / (unsigned)nb1 + 1ull) : 0u;   // p / nb1 = (p * inv1) >> 32 while p * nb1 < 2^32
 
-    // ---- phase 1a: coefficients of the candidate pixels, filed by window base
-    for (int p = tid; p < nb1 * nb2; p += NT) {
-        const int i1 = I1a + p % nb1, i2 = I2a + p / nb1;
-        T w1[S1], w2[S2];
-        int b1, b2;
-        if (!affine_coefs<T, S1, S2>(a, i1, i2, b1, b2, w1, w2)) {
-            atomicExch(err, 1);
-            continue;
-        }
-#pragma unroll
-        for (int s = 0; s < S1; ++s) sw1[p * S1 + s] = w1[s];
-#pragma unroll
-        for (int s = 0; s < S2; ++s) sw2[p * S2 + s] = w2[s];
-        const int u1 = b1 - (J1a - (S1 - 1)), u2 = b2 - (J2a - (S2 - 1));
-        // (canonical bases -(S-1) and len-1 stand for every window hanging completely over an edge: those pixels only
-        // feed border elements, and any number of them shares that base)
-        const bool sat = b1 <= -(S1 - 1) || b1 >= a.m1 - 1 || b2 <= -(S2 - 1) || b2 >= a.m2 - 1;
-        if (!sat && u1 >= 0 && u1 < CW && u2 >= 0 && u2 < CH) {
-            const int k = atomicAdd(&ccnt[u2 * CW + u1], 1);
-            if (k < KC)
-                cpix[(u2 * CW + u1) * KC + k] = (unsigned short)p;
-        }
-    }
-    __syncthreads();
-    // Cells in ascending pixel order (the atomics above filled them in any order).  A cell that received more than KC
-    // pixels keeps its KC smallest; the others go to the tile's overflow list, also in ascending order: one thread
-    // re-scans the candidates of such a cell (rare: it takes a position rounded across a cell boundary).
-    for (int c = tid; c < CW * CH; c += NT) {
-        const int n = ccnt[c];
-        unsigned short *e = cpix + c * KC;
-        if (n <= KC) {
-            if (n == 2 && e[0] > e[1]) {
-                const unsigned short t = e[0];
-                e[0] = e[1], e[1] = t;
-            }
-            continue;
-        }
-        const int u1 = c % CW, u2 = c / CW;
-        int kept = 0;
-        for (int p = 0; p < nb1 * nb2; ++p) {   // ascending pixel order
-            T w1[S1], w2[S2];
-            int b1, b2;
-            if (!affine_coefs<T, S1, S2>(a, I1a + p % nb1, I2a + p / nb1, b1, b2, w1, w2)) continue;
-            if (b1 - (J1a - (S1 - 1)) != u1 || b2 - (J2a - (S2 - 1)) != u2) continue;
-            if (kept < KC) {
-                e[kept++] = (unsigned short)p;
-            } else {
-                const int o = atomicAdd(&novf, 1);
-                if (o < AG_NOVF) {
-                    sovf[o].u1 = u1, sovf[o].u2 = u2, sovf[o].off = (p / nb1) * P + p % nb1;
-#pragma unroll
-                    for (int s = 0; s < S1; ++s) sovf[o].w1[s] = w1[s];
-#pragma unroll
-                    for (int s = 0; s < S2; ++s) sovf[o].w2[s] = w2[s];
-                } else {
-                    atomicExch(err, 4);
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 1b: this element's contributors: the pixels of cell (j1 - s1, j2 - s2) reach it with tap (s1, s2).
-    // Register slot k*S1*S2 + s2*S1 + s1 = k-th pixel of that cell (first pixels first: the second half is mostly empty);
-    // empty slots carry weight 0 and the offset of a zero word.
-    constexpr int ZOFF = -(128 / (int)sizeof(T));   // a zero word in front of every box
-    T w[CAP];
-    int off[CAP];
-    unsigned second = 0;                            // bit q: slots S1*S2 + 4q .. + 4q+3 hold something
-#pragma unroll
-    for (int s2 = 0; s2 < S2; ++s2)
-#pragma unroll
-        for (int s1 = 0; s1 < S1; ++s1) {
-            const int c = (ly + (S2 - 1) - s2) * CW + (lx + (S1 - 1) - s1);
-            const int n = min(ccnt[c], KC);
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const int slot = k * S1 * S2 + s2 * S1 + s1;
-                w[slot] = (T)0, off[slot] = ZOFF;
-                if (k < n) {
-                    const int p = cpix[c * KC + k];
-                    w[slot] = sw1[p * S1 + s1] * sw2[p * S2 + s2];
-                    off[slot] = (p / nb1) * P + p % nb1;
-                    if (k > 0) second |= 1u << ((slot - S1 * S2) / 4);
-                }
-            }
-        }
-    const int nov = min(novf, AG_NOVF);
-    __syncthreads();   // phase 1 data is dead: the boxes take its place
-
-    // ---- phase 2: per image, stage the box of src pixels and sum
-    const int cap = (P * (g.bulk ? g.HB : g.BH) + 31 + 128 / (int)sizeof(T)) & ~31;   // elements per ring slot (zero pad + box)
-    T *ring = reinterpret_cast<T *>(smem_raw);
+    // The ring of src boxes (phase 2) has its own shared memory, so the first boxes are requested NOW and arrive while
+    // phase 1 runs.  Ring slots have a compile-time stride and the image loop below is unrolled over the slots: a
+    // contributor costs one LDS with an immediate offset and one FMA.
+    constexpr int SLOT = AG_SLOTB / (int)sizeof(T);   // elements per ring slot (PADN of them: the zero pad)
+    T *ring = reinterpret_cast<T *>(smem_raw + g.ring_off);
     const int NS = g.bulk ? AG_NSTG : 1;
-    for (int k = tid; k < NS * (128 / (int)sizeof(T)); k += NT)
-        ring[(size_t)(k / (128 / (int)sizeof(T))) * cap + k % (128 / (int)sizeof(T))] = (T)0;
-    __syncthreads();
+    for (int k = tid; k < NS * PADN; k += NT) ring[(size_t)(k / PADN) * SLOT + k % PADN] = (T)0;
     const int64_t splane = (int64_t)a.n1 * a.n2, dplane = (int64_t)a.m1 * a.m2;
     const bool mine = j1 >= 1 && j1 < a.m1 - 1 && j2 >= 1 && j2 < a.m2 - 1;   // interior element of dst
     const bool hb = a.beta != (T)0;
     auto stage = [&](int64_t b, int k) {
-        T *buf = ring + (size_t)k * cap + 128 / (int)sizeof(T);
+        T *buf = ring + (size_t)k * SLOT + PADN;
         if (g.bulk) {
             if (tid == 0) {
                 mbar_expect_tx(&bar[k], (uint32_t)(g.PB * g.HB * sizeof(T)));
@@ -225,42 +143,152 @@ affine_adj_gather_kernel(AffineArgs<T> a, AGParams g, const T *__restrict__ src,
     const int64_t bstep = gridDim.z;
     const int64_t b0 = blockIdx.z;
     const int nimg = b0 < a.nbatch ? (int)((a.nbatch - b0 + bstep - 1) / bstep) : 0;
-    if (nb1 > 0 && nb2 > 0)
+    const bool any = nb1 > 0 && nb2 > 0;
+    if (any && g.bulk)
         for (int k = 0; k < NS - 1 && k < nimg; ++k) stage(b0 + k * bstep, k);
+
+    // ---- phase 1a: coefficients of the candidate pixels, filed by window base
+    for (int p = tid; p < nb1 * nb2; p += NT) {
+        const int pr = nb1 > 1 ? (int)(((unsigned long long)(unsigned)p * inv1) >> 32) : p, pc = p - pr * nb1;   // row, column in the box
+        const int i1 = I1a + pc, i2 = I2a + pr;
+        T w1[S1], w2[S2];
+        int b1, b2;
+        {   // the pixel's position, with the operations of affine_coefs; most of the bounding box lies outside the
+            // (rotated) rectangle of positions that reach the tile: those candidates stop here
+            using A = Ar<T>;
+            const T pos1 = (T)(i1 + 1), pos2 = (T)(i2 + 1);
+            const T px = A::add(A::mul(a.xx, pos1), A::add(A::mul(a.xy, pos2), a.x));
+            const T py = A::add(A::mul(a.yx, pos1), A::add(A::mul(a.yy, pos2), a.y));
+            if (px < (T)(J1a - 0.5 * S1 - 1.0) || px > (T)(J1a + TD1 + 0.5 * S1 + 2.0) || py < (T)(J2a - 0.5 * S2 - 1.0) ||
+                py > (T)(J2a + TD2 + 0.5 * S2 + 2.0))
+                continue;   // (NaN positions fall through to affine_coefs, which flags them)
+        }
+        if (!affine_coefs<T, S1, S2>(a, i1, i2, b1, b2, w1, w2)) {
+            atomicExch(err, 1);
+            continue;
+        }
+#pragma unroll
+        for (int s = 0; s < S1; ++s) sw1[p * S1 + s] = w1[s];
+#pragma unroll
+        for (int s = 0; s < S2; ++s) sw2[p * S2 + s] = w2[s];
+        const int u1 = b1 - (J1a - (S1 - 1)), u2 = b2 - (J2a - (S2 - 1));
+        // (canonical bases -(S-1) and len-1 stand for every window hanging completely over an edge: those pixels only
+        // feed border elements, and any number of them shares that base)
+        const bool sat = b1 <= -(S1 - 1) || b1 >= a.m1 - 1 || b2 <= -(S2 - 1) || b2 >= a.m2 - 1;
+        if (!sat && u1 >= 0 && u1 < CW && u2 >= 0 && u2 < CH) {
+            const int k = atomicAdd(&ccnt[u2 * CW + u1], 1);
+            if (k < KC) cpix[(u2 * CW + u1) * KC + k] = make_ushort2((unsigned short)p, (unsigned short)(pr * P + pc + PADN));
+        }
+    }
+    __syncthreads();
+    // Cells in ascending pixel order (the atomics above filled them in any order).  A cell that received more than KC
+    // pixels keeps its KC smallest; the others go to the tile's overflow list, also in ascending order: one thread
+    // re-scans the candidates of such a cell (rare: it takes a position rounded across a cell boundary).
+    for (int c = tid; c < CW * CH; c += NT) {
+        const int n = ccnt[c];
+        ushort2 *e = cpix + c * KC;
+        if (n <= KC) {
+            if (n == 2 && e[0].x > e[1].x) {
+                const ushort2 t = e[0];
+                e[0] = e[1], e[1] = t;
+            }
+            continue;
+        }
+        const int u1 = c % CW, u2 = c / CW;
+        int kept = 0;
+        for (int p = 0; p < nb1 * nb2; ++p) {   // ascending pixel order
+            T w1[S1], w2[S2];
+            int b1, b2;
+            if (!affine_coefs<T, S1, S2>(a, I1a + p % nb1, I2a + p / nb1, b1, b2, w1, w2)) continue;
+            if (b1 - (J1a - (S1 - 1)) != u1 || b2 - (J2a - (S2 - 1)) != u2) continue;
+            if (kept < KC) {
+                e[kept++] = make_ushort2((unsigned short)p, (unsigned short)((p / nb1) * P + p % nb1 + PADN));
+            } else {
+                const int o = atomicAdd(&novf, 1);
+                if (o < AG_NOVF) {
+                    sovf[o].u1 = u1, sovf[o].u2 = u2, sovf[o].off = (p / nb1) * P + p % nb1 + PADN;
+#pragma unroll
+                    for (int s = 0; s < S1; ++s) sovf[o].w1[s] = w1[s];
+#pragma unroll
+                    for (int s = 0; s < S2; ++s) sovf[o].w2[s] = w2[s];
+                } else {
+                    atomicExch(err, 4);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1b: this element's contributors: the pixels of cell (j1 - s1, j2 - s2) reach it with tap (s1, s2).
+    // Register slot k*S1*S2 + s2*S1 + s1 = k-th pixel of that cell (first pixels first: the second half is mostly empty);
+    // empty slots carry weight 0 and the offset of the zero word.  Offsets are relative to the ring slot.
+    T w[CAP];
+    int off[CAP];
+    unsigned second = 0;                            // bit q: slots S1*S2 + 4q .. + 4q+3 hold something
+    {
+        const ushort2 *cbase = cpix + ((ly + (S2 - 1)) * CW + (lx + (S1 - 1))) * KC;
+#pragma unroll
+        for (int s2 = 0; s2 < S2; ++s2)
+#pragma unroll
+            for (int s1 = 0; s1 < S1; ++s1) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const int slot = k * S1 * S2 + s2 * S1 + s1;
+                    const ushort2 e = cbase[-(s2 * CW + s1) * KC + k];
+                    w[slot] = sw1[e.x * S1 + s1] * sw2[e.x * S2 + s2];
+                    off[slot] = e.y;
+                    if (k > 0) second |= (e.y != 0 ? 1u : 0u) << ((slot - S1 * S2) / 4);
+                }
+            }
+    }
+    const int nov = min(novf, AG_NOVF);
+
     T *dp = dst + b0 * dplane + (int64_t)j2 * a.m1 + j1;
-    int ks = 0, kn = NS - 1;
-    uint32_t par = 0;
-    for (int it = 0; it < nimg; ++it) {
-        if (nb1 > 0 && nb2 > 0) {
-            if (it + NS - 1 < nimg) stage(b0 + (int64_t)(it + NS - 1) * bstep, kn);
+    const T *pk[CAP];                              // the contributors in ring slot 0
+#pragma unroll
+    for (int k = 0; k < CAP; ++k) pk[k] = ring + off[k];
+    auto one = [&](int it, auto slot_tag, uint32_t par) {   // image `it` from ring slot KS (static)
+        constexpr int KS = decltype(slot_tag)::value;
+        if (any) {
+            if (it + NS - 1 < nimg) stage(b0 + (int64_t)(it + NS - 1) * bstep, (KS + AG_NSTG - 1) % AG_NSTG % (g.bulk ? AG_NSTG : 1));
             if (g.bulk)
-                mbar_wait(&bar[ks], par);
+                mbar_wait(&bar[KS], par);
             else
                 __syncthreads();
         }
-        const T *buf = ring + (size_t)ks * cap + 128 / (int)sizeof(T);
         T acc = (T)0;
 #pragma unroll
-        for (int k = 0; k < S1 * S2; ++k) acc = fmaT(w[k], buf[off[k]], acc);
+        for (int k = 0; k < S1 * S2; ++k) acc = fmaT(w[k], pk[k][KS * SLOT], acc);
 #pragma unroll
         for (int k0 = S1 * S2; k0 < CAP; k0 += 4) {
             if (second >> ((k0 - S1 * S2) / 4) & 1u) {
 #pragma unroll
-                for (int k = k0; k < k0 + 4 && k < CAP; ++k) acc = fmaT(w[k], buf[off[k]], acc);
+                for (int k = k0; k < k0 + 4 && k < CAP; ++k) acc = fmaT(w[k], pk[k][KS * SLOT], acc);
             }
         }
         for (int o = 0; o < nov; ++o) {   // (pixels that found their cell full)
             const int s1 = lx + (S1 - 1) - sovf[o].u1, s2 = ly + (S2 - 1) - sovf[o].u2;
-            if (s1 >= 0 && s1 < S1 && s2 >= 0 && s2 < S2) acc = fmaT(sovf[o].w1[s1] * sovf[o].w2[s2], buf[sovf[o].off], acc);
+            if (s1 >= 0 && s1 < S1 && s2 >= 0 && s2 < S2)
+                acc = fmaT(sovf[o].w1[s1] * sovf[o].w2[s2], ring[(size_t)KS * SLOT + sovf[o].off], acc);
         }
         if (mine) {
             const T v = a.alpha == (T)1 ? acc : a.alpha * acc;
             *dp = hb ? fmaT(a.beta, *dp, v) : v;     // beta = 0: dst is never read
         }
         dp += dplane * bstep;
-        if (++ks == NS) ks = 0, par ^= 1u;
-        if (++kn == NS) kn = 0;
         __syncthreads();   // every thread is done with this box before it is refilled
+    };
+    __syncthreads();   // (the zero pads of the ring)
+    if (g.bulk) {
+        uint32_t par = 0;
+        for (int it0 = 0; it0 < nimg; it0 += AG_NSTG, par ^= 1u) {
+            if (it0 + 0 < nimg) one(it0 + 0, std::integral_constant<int, 0>{}, par);
+            if (it0 + 1 < nimg) one(it0 + 1, std::integral_constant<int, 1>{}, par);
+            if (it0 + 2 < nimg) one(it0 + 2, std::integral_constant<int, 2>{}, par);
+            if (it0 + 3 < nimg) one(it0 + 3, std::integral_constant<int, 3>{}, par);
+        }
+    } else {
+        for (int it = 0; it < nimg; ++it) one(it, std::integral_constant<int, 0>{}, 0u);
     }
 }
 
@@ -559,6 +587,31 @@ static int affine_cell_capacity(double xx, double xy, double yx, double yy)
     return best;
 }
 
+// wavefronts of a warp-wide load whose lane l reads column floor(l*xx + u), row floor(l*yx + v) of a box of pitch P
+// (averaged over a few offsets): the cost model of best_pitch_mod (li_affine.cuh) for one pitch
+static double pitch_cost(double xx, double yx, int P)
+{
+    double cost = 0;
+    for (int trial = 0; trial < 8; ++trial) {
+        const double u = 0.137 * trial + 0.05, v = 0.291 * trial + 0.11;
+        int addr[32];
+        for (int l = 0; l < 32; ++l) addr[l] = (int)std::floor(l * xx + u + 64) + (int)std::floor(l * yx + v + 64) * P;
+        int worst = 0;
+        for (int bank = 0; bank < 32; ++bank) {
+            int seen[32], ns = 0;
+            for (int l = 0; l < 32; ++l) {
+                if (((addr[l] % 32) + 32) % 32 != bank) continue;
+                bool dup = false;
+                for (int k = 0; k < ns; ++k) dup |= seen[k] == addr[l];
+                if (!dup) seen[ns++] = addr[l];
+            }
+            worst = std::max(worst, ns);
+        }
+        cost += worst;
+    }
+    return cost;
+}
+
 template <typename T, int S1, int S2, int TD2>
 static int launch_affine_gather_interior(const AffineArgs<T> &a, const T *src, T *dst, int *err, cudaStream_t st, bool *done)
 {
@@ -577,12 +630,24 @@ static int launch_affine_gather_interior(const AffineArgs<T> &a, const T *src, T
     if ((int64_t)(g.BW + AL) * g.BH > 60000) return LI_OK;     // (candidate ids are 16-bit)
     g.bulk = (a.n1 % AL == 0) && (((uintptr_t)src) % 16 == 0) && encode_tiled() != nullptr && a.nbatch < (1LL << 31);
     // staged box: pitch with the fewest bank conflicts for lanes walking along the inverse image of dim 1
-    int pmod = best_pitch_mod(g.ixx, g.iyx, g.bulk ? AL : 1);
     const int need1 = g.BW + (g.bulk ? AL - 1 : 0);
-    g.PB = need1 + ((pmod - need1) & 31);
+    const int slot_elems = AG_SLOTB / (int)sizeof(T) - 128 / (int)sizeof(T);
     g.HB = g.BH;
+    {   // the narrowest pitch whose bank conflicts stay within 25 % of the best one's (boxes are re-read per image: bytes first)
+        const int step = g.bulk ? AL : 1, first = (need1 + step - 1) / step * step;
+        double best = 1e30;
+        for (int pb = first; pb < first + 32; pb += step) best = std::min(best, pitch_cost(g.ixx, g.iyx, pb));
+        g.PB = first;
+        for (int pb = first; pb < first + 32; pb += step)
+            if (pitch_cost(g.ixx, g.iyx, pb) <= 1.25 * best) {
+                g.PB = pb;
+                break;
+            }
+        if (g.PB * g.HB > slot_elems) g.PB = first;
+    }
     if (g.bulk && (g.PB > 256 || g.HB > 256)) g.bulk = 0;
     if (!g.bulk) g.PB = g.BW, g.HB = g.BH;
+    if ((int64_t)g.PB * g.HB > slot_elems || (int64_t)g.PB * g.HB + 64 > 65535) return LI_OK;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     if (g.bulk) {
@@ -599,9 +664,9 @@ static int launch_affine_gather_interior(const AffineArgs<T> &a, const T *src, T
         }
     }
     const int P = g.PB;
-    const size_t phase1 = ((size_t)(g.BW + AL - 1) * g.BH * (S1 + S2) * sizeof(T) + (size_t)CW * CH * (4 + 2 * KC) + 15) & ~(size_t)15;
-    const size_t slot = (size_t)((P * g.HB + 31 + 128 / (int)sizeof(T)) & ~31) * sizeof(T);
-    const size_t smem = std::max(phase1, slot * (g.bulk ? AG_NSTG : 1)) + 128;
+    const size_t phase1 = (((size_t)(g.BW + AL - 1) * g.BH + 1) * (S1 + S2) * sizeof(T) + (size_t)CW * CH * (4 + 4 * KC) + 15) & ~(size_t)15;
+    g.ring_off = (int)((phase1 + 127) & ~(size_t)127);
+    const size_t smem = (size_t)g.ring_off + (size_t)AG_SLOTB * (g.bulk ? AG_NSTG : 1) + 128;
     if (smem > (size_t)kSmemLimit) return LI_OK;
     dim3 grid((a.m1 + TD1 - 1) / TD1, (a.m2 + TD2 - 1) / TD2, 1);
     if (grid.y > 65535) return LI_OK;
