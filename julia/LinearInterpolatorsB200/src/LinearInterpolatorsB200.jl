@@ -7,7 +7,8 @@
 module LinearInterpolatorsB200
 
 export TabulatedInterpolator, SparseInterpolator, SparseUnidimensionalInterpolator,
-    TwoDimensionalTransformInterpolator, DeviceArray
+    TwoDimensionalTransformInterpolator, DeviceArray, Comm, comm_unique_id, allreduce_sum!, adjoint_accumulate!,
+    fit_separable, sep_apply!, sep_accumulate!, rows, columns, nrows, ncols, width, convert_coordinate
 
 using InterpolationKernels
 using TwoDimensional: AffineTransform2D
@@ -25,5 +26,6 @@ include("sparse.jl")
 include("unidimensional.jl")
 include("separable.jl")
 include("nonseparable.jl")
+include("solvers.jl")
 
 end # module

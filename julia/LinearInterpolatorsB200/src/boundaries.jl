@@ -28,7 +28,20 @@ kernel_desc(ker::Kernel{T,S}) where {T<:Floats,S} =
 
 same result as the reference's `getcoefs(ker, limits(ker, len), x)`, evaluated on the device through a one-row table.
 """
-function getcoefs(ker::Kernel{T,S}, len::Integer, x) where {T<:Floats,S}
-    t = export!(Table(ker, T[convert(T, x)], len))
+function getcoefs(ker::Kernel{T,S}, len::Integer, x::T) where {T<:Floats,S}
+    t = export!(Table(ker, T[x], len))
     return (ntuple(s -> t.J[s, 1], Val(S))..., ntuple(s -> t.W[s, 1], Val(S))...)
 end
+
+
+"""
+    convert_coordinate(T, c)
+
+the reference's extension hook (src/boundaries.jl:65-74, test/runtests.jl:90-98): coordinates of any type (e.g.
+Unitful quantities through src/init.jl) are converted to the kernel's floating-point type `T` before `getcoefs`;
+packages extend it with their own methods.  Positions cross the C boundary as `T` values: `Table(ker, x, ncols)`
+calls it element by element.
+"""
+convert_coordinate(::Type{T}, c::Real) where {T<:AbstractFloat} = convert(T, c)
+getcoefs(ker::Kernel{T,S}, len::Integer, x::Real) where {T<:Floats,S} =
+    getcoefs(ker, len, convert_coordinate(T, x))

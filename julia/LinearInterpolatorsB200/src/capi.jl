@@ -80,7 +80,7 @@ mutable struct Table{T<:Floats}
 end
 
 function Table(ker::Kernel{T,S}, x::AbstractVector, ncols::Integer) where {T<:Floats,S}
-    pos = convert(Vector{T}, x)   # convert(T, X[i]) of the reference's __maketables
+    pos = T[convert_coordinate(T, xi) for xi in x]   # convert_coordinate(T, X[i]) of the reference's __maketables
     ref = Ref{Ptr{Cvoid}}(C_NULL)
     desc = Ref(kernel_desc(ker))
     check(ccall((:li_table_create, LIB), Cint,

@@ -13,13 +13,18 @@ function apply!(α::Real, ::Type{P}, ker1::Kernel{T,S1}, x1::AbstractVector{T}, 
         m1, m2 = size(dst)
     end
     d1, d2 = DeviceArray(collect(x1)), DeviceArray(collect(x2))
-    dsrc, ddst = DeviceArray(convert(Array{T}, src)), DeviceArray(convert(Array{T}, dst))
+    # device arrays are used in place; host arrays are staged (one copy each way)
+    (src isa DeviceArray) == (dst isa DeviceArray) ||
+        error("source and destination must both be host arrays or both be device arrays")
+    dsrc = src isa DeviceArray ? src : DeviceArray(convert(Array{T}, src))
+    ddst = dst isa DeviceArray ? dst : DeviceArray(convert(Array{T}, dst))
     k1, k2 = Ref(kernel_desc(ker1)), Ref(kernel_desc(ker2))
     check(ccall((:li_sep2d_otf_apply, LIB), Cint,
                 (Cint, Ptr{KernelDesc}, Ptr{Cvoid}, Int64, Ptr{KernelDesc}, Ptr{Cvoid}, Int64, Int64, Int64, Int64,
                  Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid}),
                 P === Adjoint, k1, d1, n1, k2, d2, n2, m1, m2, 1, α, dsrc, β, ddst, C_NULL))
-    copyto!(dst, Array(ddst))
+    check(ccall((:li_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+    dst isa DeviceArray || copyto!(dst, Array(ddst))
     return dst
 end
 
@@ -77,6 +82,91 @@ function sep_accumulate!(::Type{P}, ops::AbstractVector, α::Real, xs::AbstractV
                      Ptr{Ptr{Cvoid}}, Cint, Ptr{Cvoid}),
                     P === Adjoint, N, n, handles, C_NULL, 1, α, srcs, 1.0, dsts, 0, C_NULL))
         check(ccall((:li_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+    end
+    return y
+end
+
+
+# ------------------------------------------------------------------------------------------------
+# `H = A1*A2[*A3]` and `H'` through the reference's own verbs.
+#
+# LazyAlgebra builds a `Composition` for a product of mappings and applies its factors right to left with
+# `vcreate`d temporaries (two passes over memory for A1*A2, four PCIe crossings for host arrays).  When every factor
+# is a table-backed operator on its own dimension the product is ONE call of li_sep_apply[_host]: the methods below
+# intercept `vcreate` / `apply!` for such compositions, so `H*x`, `H'*y`, `apply!(α, P, H, x, scratch, β, y)` and
+# `conjgrad(H'*H, H'*y)` of the reference's users run the fused kernels unchanged.  Any other composition of these
+# operators (two factors on one dimension, a factor without a fixed dimension) is applied factor by factor, like
+# LazyAlgebra does.
+const SepComposition = LazyAlgebra.Composition{N,<:NTuple{N,PerDim}} where {N}
+factors(H::LazyAlgebra.Composition) = getfield(H, 1)          # the tuple of operands (field `ops` in LazyAlgebra 0.2)
+
+function per_dimension(H::SepComposition, ndims::Int)
+    slots = Vector{Any}(nothing, ndims)
+    for A in factors(H)
+        d = interp_dim(A)
+        (d isa Int && 1 ≤ d ≤ ndims && slots[d] === nothing) || return nothing
+        slots[d] = A
+    end
+    return slots
+end
+
+function _sep_outdims(H::SepComposition, ::Type{P}, x::AbstractArray{T,N}) where {P,T,N}
+    dims = collect(size(x))
+    for A in factors(H)
+        d = interp_dim(A)
+        d isa Int || error("dimension to interpolate must be provided")
+        1 ≤ d ≤ N || error("out of range dimension $d")
+        nin, nout = P === Direct ? (A.ncols, A.nrows) : (A.nrows, A.ncols)
+        dims[d] == nin || throw(DimensionMismatch("dimension $d of source must be $nin"))
+        dims[d] = nout
+    end
+    return Tuple(dims)
+end
+
+vcreate(::Type{P}, H::SepComposition, x::HostOrDevice{T,N}, scratch::Bool=false) where {P<:Union{Direct,Adjoint},T<:Floats,N} =
+    similar_array(x, T, _sep_outdims(H, P, x))
+
+function apply!(α::Real, ::Type{P}, H::SepComposition, x::HostOrDevice{T,N}, scratch::Bool, β::Real,
+                y::HostOrDevice{T,N}) where {P<:Union{Direct,Adjoint},T<:Floats,N}
+    size(y) == _sep_outdims(H, P, x) || throw(DimensionMismatch("incompatible destination and source dimensions"))
+    slots = per_dimension(H, N)
+    if slots !== nothing
+        return sep_apply_tables!(α, P, slots, x, β, y)
+    end
+    # generic: factor by factor (right to left for Direct, left to right for Adjoint), alpha and beta in the last one
+    fs = P === Direct ? reverse(collect(factors(H))) : collect(factors(H))
+    z = x
+    for (k, A) in enumerate(fs)
+        if k == length(fs)
+            apply!(α, P, A, z, false, β, y)
+        else
+            z = apply!(1, P, A, z, false, 0, vcreate(P, A, z, false))
+        end
+    end
+    return y
+end
+
+# li_sep_apply[_host] with one (possibly missing) table per dimension
+function sep_apply_tables!(α::Real, ::Type{P}, slots::Vector, x::HostOrDevice{T,N}, β::Real,
+                           y::HostOrDevice{T,N}) where {P<:Union{Direct,Adjoint},T,N}
+    handles = Ptr{Cvoid}[A === nothing ? C_NULL : A.table.handle for A in slots]
+    dims = Int64[size(x)...]
+    GC.@preserve slots x y begin
+        if x isa DeviceArray
+            need = Ref{Csize_t}(0)
+            check(ccall((:li_sep_workspace_bytes, LIB), Cint, (Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Int64, Ptr{Csize_t}),
+                        P === Adjoint, N, handles, dims, 1, need))
+            ws = need[] > 0 ? DeviceArray{UInt8,1}(undef, (Int(need[]),)) : nothing
+            check(ccall((:li_sep_apply, LIB), Cint,
+                        (Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Int64, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid},
+                         Csize_t, Cint, Ptr{Cvoid}),
+                        P === Adjoint, N, handles, dims, 1, α, x, β, y, ws === nothing ? C_NULL : ws.ptr, need[], 0, C_NULL))
+            check(ccall((:li_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+        else
+            check(ccall((:li_sep_apply_host, LIB), Cint,
+                        (Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Int64, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                        P === Adjoint, N, handles, dims, 1, α, x, β, y, 0, C_NULL))
+        end
     end
     return y
 end

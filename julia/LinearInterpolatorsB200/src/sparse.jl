@@ -25,6 +25,29 @@ input_size(A::SparseInterpolator) = (A.ncols,)
 coefficients(A::AbstractSparseInterpolator) = vec(export!(A.table).W)
 columns(A::AbstractSparseInterpolator) = vec(export!(A.table).J)
 
+# src/sparse.jl:65-89: the operator as an explicit sparse matrix (host side, from the exported tables)
+nrows(A::AbstractSparseInterpolator) = A.nrows
+ncols(A::AbstractSparseInterpolator) = A.ncols
+width(A::AbstractSparseInterpolator) = A.table.S
+nrows(A::TabulatedInterpolator) = A.nrows
+ncols(A::TabulatedInterpolator) = A.ncols
+width(A::TabulatedInterpolator) = getfield(A, :table).S
+function rows(A::Union{AbstractSparseInterpolator,TabulatedInterpolator})
+    S, n = width(A), nrows(A)
+    R = Vector{Int}(undef, S * n)
+    k0 = 0
+    for i in 1:n                       # R[k+s] = i, src/sparse.jl:75-82
+        for s in 1:S
+            R[k0 + s] = i
+        end
+        k0 += S
+    end
+    return R
+end
+import SparseArrays
+SparseArrays.sparse(A::Union{AbstractSparseInterpolator,TabulatedInterpolator}) =
+    SparseArrays.sparse(rows(A), vec(columns(A)), vec(coefficients(A)), nrows(A), ncols(A))   # src/sparse.jl:88-89
+
 SparseInterpolator(ker::Kernel{T}, args...) where {T<:AbstractFloat} = SparseInterpolator{T}(ker, args...)
 SparseInterpolator{T}(ker::Kernel, args...) where {T<:AbstractFloat} = SparseInterpolator{T}(T(ker), args...)
 SparseInterpolator{T}(ker::Kernel{T,S}, pos::AbstractArray{<:Real,N}, grd::AbstractRange) where {T<:Floats,S,N} =

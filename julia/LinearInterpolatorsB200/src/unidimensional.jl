@@ -9,12 +9,16 @@ function apply!(α::Number, ::Type{P}, ker::Kernel{T,S}, x::AbstractArray{<:Any,
         @assert size(src) == size(x)
     end
     len = P === Direct ? length(src) : length(dst)
-    dx, dsrc = DeviceArray(convert(Array{T}, x)), DeviceArray(convert(Array{T}, src))
-    ddst = DeviceArray(convert(Array{T}, dst))
+    (src isa DeviceArray) == (dst isa DeviceArray) ||
+        error("source and destination must both be host arrays or both be device arrays")
+    dx = x isa DeviceArray ? x : DeviceArray(convert(Array{T}, x))
+    dsrc = src isa DeviceArray ? src : DeviceArray(convert(Array{T}, src))      # (device arrays are used in place)
+    ddst = dst isa DeviceArray ? dst : DeviceArray(convert(Array{T}, dst))
     desc = Ref(kernel_desc(ker))
     check(ccall((:li_otf1d_apply, LIB), Cint,
                 (Cint, Ptr{KernelDesc}, Ptr{Cvoid}, Int64, Int64, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
                 P === Adjoint, desc, dx, length(x), len, α, dsrc, β, ddst, 0, C_NULL))
-    copyto!(dst, Array(ddst))
+    check(ccall((:li_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+    dst isa DeviceArray || copyto!(dst, Array(ddst))
     return dst
 end
