@@ -325,6 +325,8 @@ def run_b200(args):
     # become host-bound; the graphs take the host out of the timed region.  Falls back to the eager time if the
     # capture is refused.
     ms_per_step, timed_how = eager_ms_per_step, "eager calls through the public API"
+    fwd_ms_eager, adj_ms_eager = fwd_ms, adj_ms
+    per_launch_how = "CUDA events around each apply in the eager pass of the same K steps"
     try:
         graphs = []
         cap_stream = torch.cuda.Stream(dev)
@@ -348,6 +350,33 @@ def run_b200(args):
         ms_per_step = g0.elapsed_time(g1) / args.steps
         timed_how = "CUDA-graph replay of the public-API calls (one captured step per buffer set)"
         launches = 2 * args.steps
+        # per-kernel launch durations: the same launches, one kernel type per graph (back to back on the stream, the
+        # buffer sets rotating), CUDA events around K launches.  An event pair around every single eager launch adds
+        # the event records and the launch gap to a 65 us kernel (kept as *_eager_events).
+        def per_launch(which):
+            with torch.cuda.stream(cap_stream):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap_stream):
+                    for b in range(NBUF):
+                        if which == "fwd":
+                            li.apply_b(1, li.Direct, H, xs[b], False, 0, ys_out[b])
+                        else:
+                            li.apply_b(1, li.Adjoint, H, ys_in[b], False, 0, zs[b])
+            torch.cuda.current_stream(dev).wait_stream(cap_stream)
+            reps = max(2, args.steps // NBUF)
+            for _ in range(2):
+                g.replay()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            barrier()
+            return e0.elapsed_time(e1) / (reps * NBUF)
+        fwd_ms_eager, adj_ms_eager = fwd_ms, adj_ms
+        fwd_ms, adj_ms = per_launch("fwd"), per_launch("adj")
+        per_launch_how = "CUDA events around K back-to-back graph-replayed launches of one kernel (buffer sets rotating)"
     except Exception as exc:  # pragma: no cover
         timed_how += f" (graph capture refused: {type(exc).__name__})"
     if dist is not None:
@@ -445,7 +474,8 @@ def run_b200(args):
             "config": common_config(),
             "notes": {"l2": "inputs rotate over 2 buffer sets of 671 MB each (> 126 MB L2); no timed kernel re-reads fresh data",
                       "timed_region": timed_how, "eager_ms_per_step": eager_ms_per_step,
-                      "per_launch_times": "CUDA events around each apply in the eager pass of the same K steps",
+                      "per_launch_times": per_launch_how,
+                      "fwd_ms_eager_events": fwd_ms_eager, "adj_ms_eager_events": adj_ms_eager,
                       "host_wall_ms_per_step": 1e3 * t_host / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_captured_at": traffic_from,

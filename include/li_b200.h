@@ -293,7 +293,7 @@ LI_API int li_conjgrad_sep(int ndim, const li_table *const *tabs, const int64_t 
 
 /* ---- dispatch switches ------------------------------------------------------
  * Process-wide integer options, initialised once from the environment at load time (LI_B200_<NAME>): "no_fused",
- * "no_stream_dn", "no_bands", "affine_plain", "trace", "adj_debug", "no_multi".  They select slower cross-check
+ * "no_stream_dn", "no_bands", "affine_plain", "trace", "adj_debug", "no_multi", "exp".  They select slower cross-check
  * paths; the hot path never calls getenv(). */
 LI_API int li_set_option(const char *name, int value);
 LI_API int li_get_option(const char *name, int *value);

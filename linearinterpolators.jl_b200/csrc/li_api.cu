@@ -11,10 +11,10 @@ std::atomic<long long> g_launches{0};
 std::atomic<int> g_options[OPT_COUNT];
 
 static const char *const kOptionNames[OPT_COUNT] = {"no_fused", "no_stream_dn", "no_bands", "affine_plain",
-                                                    "trace", "adj_debug", "no_multi"};
+                                                    "trace", "adj_debug", "no_multi", "exp"};
 static const char *const kOptionEnv[OPT_COUNT] = {"LI_B200_NO_FUSED", "LI_B200_NO_STREAM_DN", "LI_B200_NO_BANDS",
                                                   "LI_B200_AFFINE_PLAIN", "LI_B200_TRACE", "LI_B200_ADJ_DEBUG",
-                                                  "LI_B200_NO_MULTI"};
+                                                  "LI_B200_NO_MULTI", "LI_B200_EXP"};
 // the environment is consulted once, at load time
 static const bool g_options_init = [] {
     for (int k = 0; k < OPT_COUNT; ++k) {

@@ -21,7 +21,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 // Process-wide switches of the dispatch (li_set_option / li_get_option).  Read from the environment ONCE, when the
 // library is loaded (LI_B200_NO_FUSED, LI_B200_NO_STREAM_DN, LI_B200_NO_BANDS, LI_B200_AFFINE_PLAIN, LI_B200_TRACE,
-// LI_B200_ADJ_DEBUG); the hot path only reads these atomics, never getenv().
+// LI_B200_ADJ_DEBUG, LI_B200_NO_MULTI, LI_B200_EXP); the hot path only reads these atomics, never getenv().
 enum Option {
     OPT_NO_FUSED = 0,      // fused 2-D kernels off: per-dimension passes (cross-check of the fused kernels)
     OPT_NO_STREAM_DN,      // streaming / window kernels of li_tab_apply off: generic gather kernels
@@ -30,6 +30,7 @@ enum Option {
     OPT_TRACE,             // print dispatch decisions to stderr
     OPT_ADJ_DEBUG,         // timing probes of the fused adjoint (see li_sep2d.cu)
     OPT_NO_MULTI,          // multi-frame accumulate kernel off: one launch per frame
+    OPT_EXP,               // development: bit mask of A/B switches (2: 3-D applies without the fused 3-D kernels)
     OPT_COUNT
 };
 extern std::atomic<int> g_options[OPT_COUNT];

@@ -87,14 +87,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// packed pairs: FP32x2 instructions for float (sm_100), two scalar chains for double
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ double2 fma2(double2 a, double2 b, double2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
-__device__ __forceinline__ double2 mul2(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
-__device__ __forceinline__ double2 add2(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 __device__ __forceinline__ double4a ldg4(const double4a *p)
 {
