@@ -59,6 +59,10 @@ static int make_plan(int adjoint, int ndim, const li_table *const *tabs, const i
     return LI_OK;
 }
 
+template <typename T>
+int sep3d_fused_T(int adjoint, const li_table *t1, const li_table *t2, const li_table *t3, int64_t nb, double alpha,
+                  const void *src, double beta, void *dst, cudaStream_t st, bool *done);   // li_sep3d.cuh
+
 static int sep_workspace(const SepPlan &plan, int dtype, size_t *bytes, size_t *half)
 {
     // ping-pong buffers holding every intermediate (all but the last pass's output)
@@ -97,6 +101,16 @@ static int sep_apply_impl(int adjoint, int ndim, const li_table *const *tabs, co
     if (ndim == 3 && tabs[0] && tabs[1] && !tabs[2] && variant != LI_VARIANT_ATOMIC) {
         bool done = false;
         rc = sep2d_fused_apply(adjoint, tabs[0], tabs[1], dims_other[2] * nbatch, alpha, src, beta, dst, st, &done);
+        if (rc != LI_OK || done) return rc;
+    }
+
+    // three windowed tables: one pass (li_sep3d.cuh); it declines what it cannot stage
+    if (ndim == 3 && tabs[0] && tabs[1] && tabs[2] && variant != LI_VARIANT_ATOMIC && !opt(OPT_NO_FUSED) &&
+        !(opt(OPT_EXP) & 2) && sep2d_fused_supported(tabs[0], tabs[1]) && sep2d_fused_supported(tabs[0], tabs[2])) {
+        bool done = false;
+        rc = dtype == LI_F32
+                 ? sep3d_fused_T<float>(adjoint, tabs[0], tabs[1], tabs[2], nbatch, alpha, src, beta, dst, st, &done)
+                 : sep3d_fused_T<double>(adjoint, tabs[0], tabs[1], tabs[2], nbatch, alpha, src, beta, dst, st, &done);
         if (rc != LI_OK || done) return rc;
     }
 

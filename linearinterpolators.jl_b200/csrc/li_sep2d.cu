@@ -20,213 +20,9 @@
 
 #include "li_common.cuh"
 #include "li_sep2d.cuh"
+#include "li_sep2d_fwd.cuh"
 
 namespace li {
-
-// ---------------------------------------------------------------------------------------------
-// Forward: a streaming register pipeline.
-//
-// A CTA owns a strip of TO1 = 2*NT output columns and a chunk of output rows; a thread owns two adjacent
-// output columns (i1, i1+1).  The source rows the chunk needs are streamed, in ascending order, through a
-// ring of shared-memory stages filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP)
-// issued by one thread NSTAGE-1 stages ahead.  For every source row the thread
-//   1. interpolates along dim 1 from the staged row (taps and weights in registers; the two columns share
-//      their loads whenever the table never advances by more than one column per row, i.e. any up-sampling),
-//   2. pushes the value into a window of S2 registers whose rotation is static (the row loop is unrolled by
-//      a multiple of S2),
-//   3. emits every output row whose dim-2 window has just become complete (block-uniform count).
-// The dim-1 result never touches shared memory, no source row is re-computed, and src/dst cross HBM once.
-// Flat/SafeFlat clamping is applied while staging (clamped row index for the copy, replicated edge columns).
-constexpr int FWD_NT = 256;
-#ifndef FWD_NSTAGE_
-#define FWD_NSTAGE_ 3
-#endif
-#ifndef FWD_WAVES_
-#define FWD_WAVES_ 2
-#endif
-constexpr int FWD_NSTAGE = FWD_NSTAGE_;
-constexpr int FWD_MAXCR = 256;   // output rows per chunk (one thread per row when counting completions)
-
-template <int S2>
-struct FwdK {   // source rows per stage: a multiple of S2 (static window rotation)
-    static constexpr int value = S2 == 4 ? 8 : (S2 > 4 ? S2 : (S2 == 3 ? 6 : 8));
-};
-
-template <typename T, int S1, int S2, bool PAIR, bool BETA>
-__global__ void __launch_bounds__(FWD_NT, (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : (sizeof(T) == 4 ? 3 : 2))
-sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, const int NCNT /* staged-row counters */)
-{
-    constexpr int NT = FWD_NT, TO1 = 2 * NT, K = FwdK<S2>::value, NSTAGE = FWD_NSTAGE;
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int P1 = a.F1MAX;                                  // elements per staged row (multiple of 4)
-    T *sS = reinterpret_cast<T *>(smem_raw);                 // [NSTAGE][K][P1] ring of source rows
-    T *sW2 = sS + (size_t)NSTAGE * K * P1;                   // [CR][S2]  alpha * W2
-    int *sCnt = reinterpret_cast<int *>(sW2 + (size_t)CR * S2);   // [NCNT] outputs completed by each source row
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sCnt + ((NCNT + 1) & ~1));   // [NSTAGE]
-
-    const int tid = threadIdx.x;
-    int bid = blockIdx.x;
-    const int strip = bid % a.tiles1;
-    bid /= a.tiles1;
-    const int chunk = bid % a.tiles2 + a.chunk0;
-    const int64_t batch = bid / a.tiles2;
-    const int i1_0 = strip * TO1;
-    const int i2a = chunk * CR, rows = min(CR, a.n2 - i2a);   // output rows [i2a, i2a + rows)
-    const T *src = a.src + batch * (int64_t)a.m1 * a.m2;
-    T *dst = a.dst + batch * (int64_t)a.n1 * a.n2;
-
-    // footprint (tables are monotone): staged column c <-> source column lo1a + c, staged row r <-> lo2 + r
-    const int lo1 = a.base1[i1_0], F1 = a.base1[min(i1_0 + TO1, a.n1) - 1] + S1 - lo1;
-    const int lo1a = a.vec_ok ? (lo1 & ~3) : lo1;
-    const int lo2 = a.base2[i2a];
-    const int NR = a.base2[i2a + rows - 1] + S2 - lo2;        // source rows needed
-    const int NJ = (NR + K - 1) / K;                         // stages
-    // columns of the staged row that exist in the source; the rest are replicated edge columns
-    const int cv0 = max(0, -lo1a), cv1 = min(P1, a.m1 - lo1a);
-    const bool bulk = a.vec_ok;                              // TMA bulk copies need 16-byte aligned row segments
-    const int need1 = min(P1, F1 + (lo1 - lo1a) + 1);        // staged columns actually read (incl. the spare tap)
-    const bool patch = cv0 > 0 || cv1 < need1;
-
-    for (int k = tid; k < NCNT; k += NT) sCnt[k] = 0;
-    if (tid == 0) {
-#pragma unroll
-        for (int sgi = 0; sgi < NSTAGE; ++sgi) mbar_init(&bar[sgi], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issue = [&](int j) {   // producer (one thread): stage j <- source rows lo2 + j*K .. + K-1, clamped
-        uint64_t *b = &bar[j % NSTAGE];
-        T *buf = sS + (size_t)(j % NSTAGE) * K * P1;
-        const uint32_t bytes = (uint32_t)((cv1 - cv0) * sizeof(T));
-        mbar_expect_tx(b, bytes * K);
-#pragma unroll
-        for (int r = 0; r < K; ++r) {
-            const int row = clampi(lo2 + j * K + r, a.m2 - 1);
-            bulk_g2s(buf + r * P1 + cv0, src + (int64_t)row * a.m1 + lo1a + cv0, bytes, b);
-        }
-    };
-    auto stage_manual = [&](int j) {   // unaligned sources: plain loads by every thread
-        T *buf = sS + (size_t)(j % NSTAGE) * K * P1;
-        for (int idx = tid; idx < K * P1; idx += NT) {
-            const int r = idx / P1, c = idx - r * P1;
-            const int row = clampi(lo2 + j * K + r, a.m2 - 1);
-            buf[idx] = src[(int64_t)row * a.m1 + clampi(lo1a + c, a.m1 - 1)];
-        }
-    };
-    if (bulk) {
-        if (tid == 0)
-            for (int j = 0; j < NSTAGE - 1 && j < NJ; ++j) issue(j);
-    } else {
-        for (int j = 0; j < NSTAGE - 1 && j < NJ; ++j) stage_manual(j);
-    }
-
-    // completion counters and dim-2 weights of the chunk
-    for (int k = tid; k < rows; k += NT) atomicAdd(&sCnt[a.base2[i2a + k] - lo2 + S2 - 1], 1);
-    for (int k = tid; k < rows * S2; k += NT) sW2[k] = a.alpha * a.W2[(int64_t)i2a * S2 + k];
-
-    // per-thread dim-1 taps
-    const int colA = i1_0 + 2 * tid;
-    const bool haveA = colA < a.n1, haveB = colA + 1 < a.n1;
-    const int iA = min(colA, a.n1 - 1), iB = min(colA + 1, a.n1 - 1);
-    const int offA = a.base1[iA] - lo1a, offB = a.base1[iB] - lo1a;
-    T w1A[S1], w1B[S1];
-#pragma unroll
-    for (int s = 0; s < S1; ++s) {
-        w1A[s] = a.W1[(int64_t)iA * S1 + s];
-        w1B[s] = a.W1[(int64_t)iB * S1 + s];
-    }
-    const bool shift = offB != offA;   // PAIR: offB - offA is 0 or 1
-    const bool vec = a.vec_ok && haveB;
-    const T *wp = sW2;                                  // weights of the next output row
-    T *dp = dst + (int64_t)i2a * a.n1 + colA;           // next output element
-    T hA[S2], hB[S2];
-#pragma unroll
-    for (int s = 0; s < S2; ++s) hA[s] = hB[s] = (T)0;
-
-    for (int j = 0; j < NJ; ++j) {
-        __syncthreads();   // every thread is done with stage j-1: its buffer may be refilled
-        if (bulk) {
-            if (tid == 0 && j + NSTAGE - 1 < NJ) issue(j + NSTAGE - 1);
-            mbar_wait(&bar[j % NSTAGE], (uint32_t)((j / NSTAGE) & 1));
-        } else if (j + NSTAGE - 1 < NJ) {
-            stage_manual(j + NSTAGE - 1);   // (visible after the next barrier; stage j was written two barriers ago)
-        }
-        T *buf = sS + (size_t)(j % NSTAGE) * K * P1;
-        if (bulk && patch) {   // replicate the first / last source column into the out-of-range staged columns
-            const int warp = tid >> 5, lane = tid & 31;   // warp <-> staged row, lane <-> column to patch
-            if (warp < K) {
-                T *row = buf + warp * P1;
-                if (lane < cv0) row[lane] = row[cv0];
-                for (int c = cv1 + lane; c < need1; c += 32) row[c] = row[cv1 - 1];
-            }
-            __syncthreads();
-        }
-        if (!haveA) continue;
-        const int *cp = sCnt + j * K;
-        // pass 1: dim 1, for the K staged rows at once (independent FMA chains)
-        T nA[K], nB[K];
-#pragma unroll
-        for (int u = 0; u < K; ++u) {
-            if constexpr (PAIR) {
-                const T *p = buf + u * P1 + offA;
-                T v[S1 + 1];
-#pragma unroll
-                for (int s = 0; s <= S1; ++s) v[s] = p[s];
-                T accA = v[0] * w1A[0];
-                T accB = (shift ? v[1] : v[0]) * w1B[0];
-#pragma unroll
-                for (int s = 1; s < S1; ++s) {
-                    accA = fmaT(v[s], w1A[s], accA);
-                    accB = fmaT(shift ? v[s + 1] : v[s], w1B[s], accB);
-                }
-                nA[u] = accA, nB[u] = accB;
-            } else {
-                const T *p = buf + u * P1 + offA, *q = buf + u * P1 + offB;
-                T accA = p[0] * w1A[0];
-                T accB = q[0] * w1B[0];
-#pragma unroll
-                for (int s = 1; s < S1; ++s) {
-                    accA = fmaT(p[s], w1A[s], accA);
-                    accB = fmaT(q[s], w1B[s], accB);
-                }
-                nA[u] = accA, nB[u] = accB;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < K; ++u) {
-            hA[u % S2] = nA[u];
-            hB[u % S2] = nB[u];
-            // pass 2: emit the output rows whose window [row-S2+1, row] is now complete
-#pragma unroll 1
-            for (int n = cp[u]; n > 0; --n) {
-                T w2[S2];
-                ld_weights<T, S2>(wp, w2);
-                wp += S2;
-                T oA = hA[(u + 1) % S2] * w2[0], oB = hB[(u + 1) % S2] * w2[0];
-#pragma unroll
-                for (int s = 1; s < S2; ++s) {
-                    oA = fmaT(hA[(u + 1 + s) % S2], w2[s], oA);
-                    oB = fmaT(hB[(u + 1 + s) % S2], w2[s], oB);
-                }
-                if constexpr (BETA) {
-                    oA = fmaT(a.beta, dp[0], oA);
-                    if (haveB) oB = fmaT(a.beta, dp[1], oB);
-                }
-                if (vec) {
-                    Pack<T, 2> o;
-                    o.v[0] = oA, o.v[1] = oB;
-                    st_pack<T, 2>(dp, o);
-                } else {
-                    dp[0] = oA;
-                    if (haveB) dp[1] = oB;
-                }
-                dp += a.n1;
-            }
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Adjoint: the transpose of the forward operator, tile-owned and atomic-free.
@@ -645,68 +441,6 @@ int sep2d_num_sms()
     int &n = cache[dev];
     if (!n && (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)) n = 148;
     return n;
-}
-
-template <typename T, int S1, int S2>
-static int launch_fwd(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64_t nbatch, cudaStream_t st,
-                      bool *done)
-{
-    constexpr int TO1 = 2 * FWD_NT, K = FwdK<S2>::value;
-    a.tiles1 = (a.n1 + TO1 - 1) / TO1;
-    // chunks of output rows: FWD_WAVES_ whole waves of the CTAs resident per SM (the kernel's launch bound), chunk
-    // length a multiple of 8 and at most FWD_MAXCR
-    constexpr int PER_SM = (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : (sizeof(T) == 4 ? 3 : 2);
-    const int64_t target = (int64_t)sep2d_num_sms() * PER_SM * FWD_WAVES_;
-    int chunks = (int)std::max<int64_t>(1, target / (a.tiles1 * nbatch));   // (rounded down: whole waves)
-    int CR = (a.n2 + chunks - 1) / chunks;
-    CR = std::min(FWD_MAXCR, std::max(8, (CR + 7) & ~7));
-    a.tiles2 = (a.n2 + CR - 1) / CR;
-    int span1 = 0, span2 = 0;
-    int rc = table_fwd_span(t1, TO1, st, &span1);
-    if (rc == LI_OK) rc = table_fwd_span(t2, CR, st, &span2);
-    if (rc != LI_OK) return rc;
-    // staged row: footprint + 1 spare tap (paired load) + up to 3 columns of alignment shift, multiple of 4
-    a.F1MAX = (span1 + S1 + 1 + 3 + 3) & ~3;
-    const int NCNT = (span2 + S2 + K - 1) / K * K;   // staged source rows of a chunk, padded to whole stages
-    // 16-byte bulk copies need aligned source rows; 8-byte stores need aligned destination rows
-    a.vec_ok = (a.m1 % 4 == 0) && (((uintptr_t)a.src) % 16 == 0) && (a.n1 % 2 == 0) &&
-               (((uintptr_t)a.dst) % (2 * sizeof(T)) == 0);
-    const size_t smem = ((size_t)FWD_NSTAGE * K * a.F1MAX + (size_t)CR * S2) * sizeof(T) +
-                        (size_t)((NCNT + 1) & ~1) * sizeof(int) + FWD_NSTAGE * sizeof(uint64_t);
-    if (smem > (size_t)kSmemLimit) return LI_OK;   // footprint too large for staging: decline
-    if (BandCtl *bc = sep2d_band()) {   // host-buffer pipeline: describe the chunks, or launch a band of them
-        if (bc->mode == 1) {
-            const std::vector<int32_t> *bh = nullptr;
-            rc = table_base_host(t2, st, &bh);
-            if (rc != LI_OK) return rc;
-            bc->row_begin.assign(a.tiles2 + 1, a.n2);
-            bc->src_end.assign(a.tiles2, 0);
-            for (int k = 0; k < a.tiles2; ++k) {
-                bc->row_begin[k] = k * CR;
-                const int last = std::min((k + 1) * CR, a.n2) - 1;
-                bc->src_end[k] = std::min(std::max((*bh)[last] + S2 - 1, 0), a.m2 - 1) + 1;
-            }
-            *done = true;
-            return LI_OK;
-        }
-        a.chunk0 = bc->chunk0;
-        a.tiles2 = bc->nchunks;
-    }
-    const int64_t blocks = (int64_t)a.tiles1 * a.tiles2 * nbatch;
-    LI_REQUIRE(blocks <= 0x7fffffffLL, LI_ERR_UNSUPPORTED, "too many tiles");
-    const bool pair = t1->max_step <= 1, beta = a.beta != (T)0;
-#define LI_FWD(P, B)                                                          \
-    if (pair == P && beta == B) {                                             \
-        auto kern = sep2d_fwd_kernel<T, S1, S2, P, B>;                        \
-        rc = set_smem(kern, smem);                                            \
-        if (rc != LI_OK) return rc;                                           \
-        kern<<<(unsigned)blocks, FWD_NT, smem, st>>>(a, CR, NCNT);            \
-    }
-    LI_FWD(true, false) LI_FWD(true, true) LI_FWD(false, false) LI_FWD(false, true)
-#undef LI_FWD
-    LI_CHECK_LAUNCH();
-    *done = true;
-    return LI_OK;
 }
 
 template <typename T, int S1, int S2>

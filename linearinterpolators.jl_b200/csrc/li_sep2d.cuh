@@ -83,6 +83,13 @@ struct SepArgs {
     T alpha, beta;
     const T *src;
     T *dst;
+    // three dimensions (li_sep3d.cuh): the table along dim 3; n3 rows (fine side), m3 columns
+    const int32_t *base3;          // window bases
+    const T *W3;                   // forward: [n3*S3] weights
+    const int32_t *bp3, *bfold3;   // adjoint: bptr table (rows feeding a column), folded bases
+    const T *W3f;                  // adjoint: folded weights
+    int n3, m3, S3;
+    int nc3;                       // planes combined into one staged row (forward: S3; adjoint: most rows feeding a plane)
 };
 
 

@@ -54,16 +54,29 @@ constexpr int ADS_NSTAGE = ADS_NSTAGE_;
 #endif
 constexpr int ADS_PER_SM = ADS_OCC_ * 256 / ADS_NT;   // CTAs per SM of the 4-byte, <= 10-tap kernels
 
-template <int S2>
+template <int S2, bool D3 = false>
 struct AdsK {   // src rows per stage: a multiple of 2*S2 so that the static schedule has whole slot rotations
-    static constexpr int value = (S2 == 6 || S2 == 3) ? 12 : ADS_K_;
+    static constexpr int value = D3 ? ((S2 == 6 || S2 == 3) ? 6 : 4) : ((S2 == 6 || S2 == 3) ? 12 : ADS_K_);
 };
+#ifndef ADS3_NSR_
+#define ADS3_NSR_ 2
+#endif
+constexpr int ADS3_NSR = ADS3_NSR_;   // D3: stages of the ring of raw src rows
+constexpr int ADS3_NC = 4;            // D3: most src planes feeding one dst plane
 
-template <typename T, int S1, int S2, int NU, int R>
+// D3 = true: a third table along dim 3, (A1*A2*A3)'.  The "batch" index of the grid is a dst plane j3; its staged rows
+// are the combinations  sum_i W3f[i, j3 - bfold3[i]] * src[:, row, i]  over the src planes i feeding that dst plane (a
+// block-uniform list of at most ADS3_NC planes, ascending = the order of the reference's scatter along dim 3): the raw
+// rows land in a second ring (TMA bulk copies, one per plane and row) and every thread combines a few 16-byte vectors
+// of stage j+1 into the row buffer while stage j is consumed.  Only the generic schedule (R = 0) is built.
+template <typename T, int S1, int S2, int NU, int R, bool D3>
 __global__ void __launch_bounds__(ADS_NT, (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? ADS_PER_SM : ADS_PER_SM / 2)
 sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 {
-    constexpr int NT = ADS_NT, K = AdsK<S2>::value, NSTAGE = ADS_NSTAGE;
+    constexpr int NT = ADS_NT, K = AdsK<S2, D3>::value;
+    constexpr int NSTAGE = D3 ? 2 : ADS_NSTAGE;              // row buffers the pipeline reads
+    constexpr int NBAR = D3 ? ADS3_NSR : ADS_NSTAGE;         // stages filled by TMA
+    static_assert(!D3 || R == 0, "the 3-D form runs the generic schedule");
     constexpr int V = 2;   // elements per shared-memory load of the gather: LDS.64 for float, LDS.128 for double
     static_assert(NU % V == 0 && NU >= 4 && NU % 2 == 0, "bad NU");
     static_assert(R == 0 || (K % R == 0 && (K / R) % S2 == 0), "bad stage size");
@@ -71,9 +84,10 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int P1 = a.F1MAX;                                  // elements per staged row (multiple of 16 bytes)
     T *sS = reinterpret_cast<T *>(smem_raw);                 // [NSTAGE][K][P1]
-    T *sW2 = sS + (size_t)NSTAGE * K * P1;                   // [NRMAX][S2] alpha * folded dim-2 weights
+    T *sR = sS + (size_t)NSTAGE * K * P1;                    // D3: [NBAR][nc3][K][P1] ring of raw rows
+    T *sW2 = sR + (size_t)(D3 ? NBAR * a.nc3 : 0) * K * P1;  // [NRMAX][S2] alpha * folded dim-2 weights
     int *sNv = reinterpret_cast<int *>(sW2 + (size_t)NRMAX * S2);   // [CR + 2*S2] src rows whose window starts at a dst row
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sNv + ((CR + 2 * S2 + 1) & ~1));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sNv + ((CR + 2 * S2 + 1) & ~1));   // [NBAR]
 
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -85,8 +99,30 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
     const int va = a.cstart[chunk], vb = a.cstart[chunk + 1];   // owned dst rows (chunks of about equal cost, <= CR rows)
     if (va >= vb) return;                                    // (empty chunk: block-uniform, before any barrier)
     const int v0 = va - (S2 - 1);                            // first dst row the chunk's src rows reach
-    const T *src = a.src + batch * (int64_t)a.n1 * a.n2;
+    const int64_t plane = (int64_t)a.n1 * a.n2;
+    const T *src = a.src + (D3 ? (batch / a.m3) * a.n3 : batch) * plane;
     T *dst = a.dst + batch * (int64_t)a.m1 * a.m2;
+    // D3: the src planes feeding dst plane j3 and their folded weights (block-uniform, every thread its own copy)
+    int nc = 0;
+    int pl3[ADS3_NC];
+    T w3[ADS3_NC];
+    if constexpr (D3) {
+        const int j3 = (int)(batch % a.m3);
+        const int f0 = j3 == 0 ? 0 : a.bp3[j3], f1 = j3 == a.m3 - 1 ? a.n3 : a.bp3[j3 + a.S3];
+#pragma unroll
+        for (int t = 0; t < ADS3_NC; ++t) pl3[t] = 0, w3[t] = (T)0;
+        for (int i = f0; i < f1; ++i) {
+            const int b = a.base3[i];
+            if (j3 >= clampi(b, a.m3 - 1) && j3 <= clampi(b + a.S3 - 1, a.m3 - 1)) {
+                const T w = a.W3f[(int64_t)i * a.S3 + (j3 - a.bfold3[i])];
+#pragma unroll
+                for (int t = 0; t < ADS3_NC; ++t)
+                    if (t == nc) pl3[t] = i, w3[t] = w;
+                ++nc;
+            }
+        }
+        nc = min(nc, ADS3_NC);   // (the launcher checked the table: never more)
+    }
 
     const int u_lo = c0 == 0 ? 0 : a.bp1[c0];                // first src column with a tap in the strip
     constexpr int AL = 16 / (int)sizeof(T);
@@ -99,21 +135,91 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 
     if (tid == 0) {
 #pragma unroll
-        for (int sgi = 0; sgi < NSTAGE; ++sgi) mbar_init(&bar[sgi], 1);
+        for (int sgi = 0; sgi < NBAR; ++sgi) mbar_init(&bar[sgi], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int j) {   // producer (one thread): stage j <- src rows i2lo + j*K ..
-        uint64_t *b = &bar[j % NSTAGE];
-        T *buf = sS + (size_t)(j % NSTAGE) * K * P1;
+    // D3: the copies of a stage are shared out over the warps (lane 0 of warp w sends copy q = w, w + NT/32, ..: one or
+    // two per stage, so that no warp falls behind the others); what does not change from stage to stage is kept in
+    // registers.  A dst plane that nothing feeds still runs the pipeline, on plane 0.
+    constexpr int NQ = D3 ? (ADS3_NC * K + NT / 32 - 1) / (NT / 32) : 1;
+    const T *gq[NQ];
+    int rq[NQ];
+    uint32_t sq[NQ];
+    const uint32_t bar0 = smem_u32(bar);
+    const int ncc = max(nc, 1);
+    if constexpr (D3) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            const int q = (tid >> 5) + i * (NT / 32);
+            const int t = q / K, r = q - t * K;
+            rq[i] = q < ncc * K ? r : K;   // (K: never sent)
+            int pl = pl3[0];
+#pragma unroll
+            for (int u = 1; u < ADS3_NC; ++u) pl = t == u ? pl3[u] : pl;
+            gq[i] = src + pl * plane + (int64_t)(i2lo + r) * a.n1 + ulo_a;
+            sq[i] = smem_u32(sR + (size_t)q * P1);
+        }
+    }
+    auto issue = [&](int j) {   // producer: stage j <- src rows i2lo + j*K ..
         const uint32_t bytes = (uint32_t)(cv1 * sizeof(T));
         const int nr = min(K, NR - j * K);
-        mbar_expect_tx(b, bytes * nr);
-        for (int r = 0; r < nr; ++r)
-            bulk_g2s(buf + r * P1, src + (int64_t)(i2lo + j * K + r) * a.n1 + ulo_a, bytes, b);
+        if constexpr (D3) {     // (lane 0 of every warp)
+            const uint32_t slot = (uint32_t)(j % NBAR);
+            const uint32_t b = bar0 + slot * 8u, so = slot * (uint32_t)(a.nc3 * K * P1 * sizeof(T));
+            if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes * nr * ncc) : "memory");
+#pragma unroll
+            for (int i = 0; i < NQ; ++i)
+                if (rq[i] < nr)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     sq[i] + so),
+                                 "l"(gq[i] + (int64_t)j * K * a.n1), "r"(bytes), "r"(b)
+                                 : "memory");
+        } else {                // (one thread)
+            uint64_t *b = &bar[j % NBAR];
+            T *buf = sS + (size_t)(j % NSTAGE) * K * P1;
+            mbar_expect_tx(b, bytes * nr);
+            for (int r = 0; r < nr; ++r)
+                bulk_g2s(buf + r * P1, src + (int64_t)(i2lo + j * K + r) * a.n1 + ulo_a, bytes, b);
+        }
     };
-    if (tid == 0)
-        for (int j = 0; j < NSTAGE - 1 && j < NJ; ++j) issue(j);
+    // D3: row buffer j <- sum over the feeding planes of raw stage j, ascending plane order; a dst plane without
+    // feeders gets zeros (never 0 * src: a non-finite sample reaches only the elements it feeds in the reference)
+    const int KP = K * P1;
+    auto combine_nc = [&](int j, auto NCt) {
+        constexpr int NC = decltype(NCt)::value;
+        const T *raw = sR + (size_t)(j % NBAR) * a.nc3 * KP;
+        T *out = sS + (size_t)(j % NSTAGE) * KP;
+        for (int idx = 4 * tid; idx < KP; idx += 4 * NT) {
+            Pack<T, 4> acc;
+            if constexpr (NC > 0) {
+                acc = ld_pack<T, 4>(raw + idx);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc.v[e] *= w3[0];
+#pragma unroll
+                for (int t = 1; t < NC; ++t) {
+                    const Pack<T, 4> q = ld_pack<T, 4>(raw + t * KP + idx);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc.v[e] = fmaT(w3[t], q.v[e], acc.v[e]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc.v[e] = (T)0;
+            }
+            st_pack<T, 4>(out + idx, acc);
+        }
+    };
+    auto combine = [&](int j) {
+        switch (nc) {
+        case 0: combine_nc(j, std::integral_constant<int, 0>{}); break;
+        case 1: combine_nc(j, std::integral_constant<int, 1>{}); break;
+        case 2: combine_nc(j, std::integral_constant<int, 2>{}); break;
+        case 3: combine_nc(j, std::integral_constant<int, 3>{}); break;
+        default: combine_nc(j, std::integral_constant<int, 4>{}); break;
+        }
+    };
+    if (D3 ? (tid & 31) == 0 : tid == 0)
+        for (int j = 0; j < (D3 ? NBAR : NSTAGE - 1) && j < NJ; ++j) issue(j);
 
     // chunk metadata: rows per dst row (generic loop only), dim-2 weights
     const int NV = vb - v0;                                   // dst rows v0 .. vb-1
@@ -228,9 +334,18 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
         }
     };
     auto next_stage = [&](int j) {   // block-uniform; returns the first staged row of stage j (this thread's window)
-        __syncthreads();             // every thread is done with stage j-1: its buffer may be refilled
-        if (tid == 0 && j + NSTAGE - 1 < NJ) issue(j + NSTAGE - 1);
-        mbar_wait(&bar[j % NSTAGE], (uint32_t)((j / NSTAGE) & 1));
+        if constexpr (D3) {
+            // stage j is combined into its row buffer now (the buffer's last readers passed the previous barrier);
+            // its raw slot is refilled after the barrier.  The copies run NBAR stages ahead of the arithmetic.
+            mbar_wait(&bar[j % NBAR], (uint32_t)((j / NBAR) & 1));
+            combine(j);
+            __syncthreads();
+            if ((tid & 31) == 0 && j + NBAR < NJ) issue(j + NBAR);
+        } else {
+            __syncthreads();             // every thread is done with stage j-1: its buffer may be refilled
+            if (tid == 0 && j + NSTAGE - 1 < NJ) issue(j + NSTAGE - 1);
+            mbar_wait(&bar[j % NSTAGE], (uint32_t)((j / NSTAGE) & 1));
+        }
         return (const T *)(sS + (size_t)(j % NSTAGE) * K * P1 + off);
     };
     // beta != 0: the old values of the thread's dst column are read S2 rows ahead of their use (slot = row mod S2,
@@ -365,10 +480,10 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 }
 
 // ---------------------------------------------------------------------------------------------
-template <typename T, int S1, int S2, int NU, int R>
+template <typename T, int S1, int S2, int NU, int R, bool D3>
 static int launch_stream(SepArgs<T> &a, int CR, int NRMAX, size_t smem, int64_t blocks, cudaStream_t st)
 {
-    auto kern = sep2d_adj_stream_kernel<T, S1, S2, NU, R>;
+    auto kern = sep2d_adj_stream_kernel<T, S1, S2, NU, R, D3>;
     int rc = set_smem(kern, smem);
     if (rc != LI_OK) return rc;
     kern<<<(unsigned)blocks, ADS_NT, smem, st>>>(a, CR, NRMAX);
@@ -379,7 +494,7 @@ static int launch_stream(SepArgs<T> &a, int CR, int NRMAX, size_t smem, int64_t 
 
 // resident CTAs per SM of one kernel instance with `smem` bytes of dynamic shared memory (registers decide for the
 // wide instances); cached per instance
-template <typename T, int S1, int S2, int NU, int R>
+template <typename T, int S1, int S2, int NU, int R, bool D3>
 static int stream_occupancy(size_t smem)
 {
     static thread_local int cached = 0, cached_dev = -1;
@@ -387,7 +502,7 @@ static int stream_occupancy(size_t smem)
     const int dev = current_device();
     if (cached && cached_smem == smem && cached_dev == dev) return cached;
     cached_dev = dev;
-    auto kern = sep2d_adj_stream_kernel<T, S1, S2, NU, R>;
+    auto kern = sep2d_adj_stream_kernel<T, S1, S2, NU, R, D3>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ADS_NT, smem) != cudaSuccess || occ < 1) {
@@ -398,10 +513,14 @@ static int stream_occupancy(size_t smem)
     return occ;
 }
 
-template <typename T, int S1, int S2>
+// (D3: nbatch counts dst planes, i.e. m3 times the number of 3-D arrays; a.base3 / bp3 / bfold3 / W3f / n3 / m3 / S3 /
+// nc3 are set)
+template <typename T, int S1, int S2, bool D3 = false>
 static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64_t nbatch, cudaStream_t st, bool *done)
 {
-    constexpr int V = 2, AL = 16 / (int)sizeof(T), K = AdsK<S2>::value;
+    constexpr int V = 2, AL = 16 / (int)sizeof(T), K = AdsK<S2, D3>::value;
+    constexpr int NROWBUF = D3 ? 2 : ADS_NSTAGE, NBAR = D3 ? ADS3_NSR : ADS_NSTAGE;
+    const size_t stage_elems = (size_t)(NROWBUF + (D3 ? NBAR * a.nc3 : 0)) * K;   // staged rows of all rings
     constexpr int NU_S = (S1 + 2 + 1) & ~1, NU_L = 2 * S1 + 2;   // taps kept per thread: same-rate / 2x operators
     if (a.m1 < S1 || a.m2 < S2) return LI_OK;                    // folding needs a full window inside the array
     if (a.n1 % AL != 0 || ((uintptr_t)a.src) % 16 != 0) return LI_OK;   // bulk copies need 16-byte aligned row segments
@@ -424,13 +543,16 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     // chunks of dst rows: about ADS_PER_SM CTAs per SM (a thread walks its rows one after the other, so a small problem
     // cut into few long chunks is latency-bound), but at least 4*S2 rows per chunk (each chunk re-reads S2-1 halo rows)
     // (the grid is sized for the CTAs that are really resident: the wide instances hold 2 or 3 per SM, not 4)
-    const int R = (t2->irrp && (t2->reg_R == 1 || t2->reg_R == 2)) ? t2->reg_R : 0;
+    const int R = (!D3 && t2->irrp && (t2->reg_R == 1 || t2->reg_R == 2)) ? t2->reg_R : 0;
     int occ = ADS_PER_SM;
     {
-        const size_t smem_est = ((size_t)ADS_NSTAGE * K * P1) * sizeof(T) + 8 * 1024;
+        const size_t smem_est = (stage_elems * P1) * sizeof(T) + 8 * 1024;
 #define LI_OCC(NUU, RR) \
-    if (NU == NUU && R == RR) occ = stream_occupancy<T, S1, S2, NUU, RR>(smem_est);
-        LI_OCC(NU_S, 0) LI_OCC(NU_S, 1) LI_OCC(NU_S, 2) LI_OCC(NU_L, 0) LI_OCC(NU_L, 1) LI_OCC(NU_L, 2)
+    if (NU == NUU && R == RR) occ = stream_occupancy<T, S1, S2, NUU, RR, D3>(smem_est);
+        LI_OCC(NU_S, 0) LI_OCC(NU_L, 0)
+        if constexpr (!D3) {
+            LI_OCC(NU_S, 1) LI_OCC(NU_S, 2) LI_OCC(NU_L, 1) LI_OCC(NU_L, 2)
+        }
 #undef LI_OCC
     }
     occ = std::min(occ, ADS_PER_SM);
@@ -439,7 +561,9 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     const int64_t target = (int64_t)sep2d_num_sms() * occ * rounds * ADS_WAVES_;
     // (rounded DOWN: a grid slightly larger than the resident slots would put its last CTAs into a second round and
     // nearly double the kernel time -- measured on 8192^2 at rate 1: 608 CTAs on 592 slots)
-    const int chunks = (int)std::max<int64_t>(1, target / (a.tiles1 * nbatch));
+    int chunks = (int)std::max<int64_t>(1, target / (a.tiles1 * nbatch));
+    // (many planes: chunks of at most 256 dst rows keep the per-chunk tables in shared memory small)
+    if (D3) chunks = std::max(chunks, (a.m2 + 255) / 256);
     // (at least 4*S2 rows per chunk: each chunk re-reads S2-1 halo rows)
     const int nchunks = std::max(1, std::min(chunks, a.m2 / std::max(8, 4 * S2)));
     a.tiles2 = nchunks;
@@ -451,13 +575,13 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     if (rc != LI_OK) return rc;
     if (CR > 4096) return LI_OK;
     const int NRMAX = (std::max(nrmax, 1) + 1) & ~1;
-    const size_t smem = ((size_t)ADS_NSTAGE * K * P1 + (size_t)NRMAX * S2) * sizeof(T) +
-                        (size_t)((CR + 2 * S2 + 1) & ~1) * sizeof(int) + ADS_NSTAGE * sizeof(uint64_t);
+    const size_t smem = (stage_elems * P1 + (size_t)NRMAX * S2) * sizeof(T) +
+                        (size_t)((CR + 2 * S2 + 1) & ~1) * sizeof(int) + NBAR * sizeof(uint64_t);
     if (trace)
-        fprintf(stderr, "[li_b200] adj stream: NU %d P1 %d CR %d NRMAX %d smem %zu tiles %d x %d R %d occ %d\n", NU, P1, CR,
-                NRMAX, smem, a.tiles1, a.tiles2, R, occ);
+        fprintf(stderr, "[li_b200] adj stream%s: NU %d P1 %d CR %d NRMAX %d smem %zu tiles %d x %d x %lld R %d occ %d\n",
+                D3 ? " 3-D" : "", NU, P1, CR, NRMAX, smem, a.tiles1, a.tiles2, (long long)nbatch, R, occ);
     if (smem > (size_t)kSmemLimit) return LI_OK;
-    if (BandCtl *bc = sep2d_band()) {   // host-buffer pipeline: describe the chunks, or launch a band of them
+    if (BandCtl *bc = D3 ? nullptr : sep2d_band()) {   // host-buffer pipeline: describe the chunks, or launch a band of them
         if (bc->mode == 1) {
             bc->row_begin.assign(plan->starts_host.begin(), plan->starts_host.end());
             bc->src_end.assign(plan->src_end_host.begin(), plan->src_end_host.end());
@@ -476,8 +600,11 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     if (opt(OPT_ADJ_DEBUG) == 4) a.vec_ok = 77;
 #endif
 #define LI_ADS(NUU, RR) \
-    if (NU == NUU && R == RR) rc = launch_stream<T, S1, S2, NUU, RR>(a, CR, NRMAX, smem, blocks, st);
-    LI_ADS(NU_S, 0) LI_ADS(NU_S, 1) LI_ADS(NU_S, 2) LI_ADS(NU_L, 0) LI_ADS(NU_L, 1) LI_ADS(NU_L, 2)
+    if (NU == NUU && R == RR) rc = launch_stream<T, S1, S2, NUU, RR, D3>(a, CR, NRMAX, smem, blocks, st);
+    LI_ADS(NU_S, 0) LI_ADS(NU_L, 0)
+    if constexpr (!D3) {
+        LI_ADS(NU_S, 1) LI_ADS(NU_S, 2) LI_ADS(NU_L, 1) LI_ADS(NU_L, 2)
+    }
 #undef LI_ADS
     if (rc == LI_OK) *done = true;
     return rc;

@@ -50,10 +50,11 @@ def sep_apply_tables(adjoint: bool, tabs, alpha, x, beta, y, owner=None, nbatch_
     check_same_kind(x, y)
     handles = (C.c_void_p * n)(*[t.handle if t is not None else None for t in tabs])
     if ar.is_device(y):
-        # two tables on dimensions 1 and 2 (plus untouched / batch dimensions) normally run as ONE fused kernel that
-        # needs no workspace: try that first, and only size the scratch of the per-dimension passes if it declines
+        # two tables on dimensions 1 and 2 (plus untouched / batch dimensions), or three tables on dimensions 1, 2, 3,
+        # normally run as ONE fused kernel that needs no workspace: try that first, and only size the scratch of the
+        # per-dimension passes if it declines
         if variant != _lib.VARIANT_ATOMIC and n >= 2 and tabs[0] is not None and tabs[1] is not None \
-                and all(t is None for t in tabs[2:]):
+                and (all(t is None for t in tabs[2:]) or (n == 3 and tabs[2] is not None)):
             status = _lib.lib.li_sep_apply(int(adjoint), n, handles, other, nbatch, float(alpha), ar.data_ptr(x),
                                            float(beta), ar.data_ptr(y), None, 0, variant, ar.current_stream(y))
             if status == _lib.OK:

@@ -631,6 +631,93 @@ def test_separable_3d_passes(li):
     assert_close(li.to_host(H.adj * li.to_device(y)), refa, T, factor=64)
 
 
+# (name, m, n, kernel entries per dim, condition, position range per dim as (first, last) in units of the source grid,
+#  fused forward expected, fused adjoint expected)
+FUSED3D_CASES = [
+    # config #4 in small: (cubic B-spline, Mitchell-Netravali, linear), rate 0.98, offsets
+    ("cfg4", (64, 40, 24), (64, 40, 24), (3, 7, 1), O.FLAT, None, True, True),
+    # 2x up-sampling everywhere, positions hanging over both ends of every dimension (clamped windows, folded planes)
+    ("up2", (32, 20, 12), (64, 41, 26), (8, 4, 4), O.SAFEFLAT, (-1.5, 2.5), True, False),
+    # linear everywhere
+    ("lin", (16, 16, 16), (24, 20, 18), (1, 1, 1), O.SAFEFLAT, (0.25, 0.5), True, True),
+    # 3x along dim 3: more than 4 planes feed one dst plane -> the adjoint declines (two passes), the forward is fused
+    ("up3", (32, 12, 8), (32, 12, 25), (3, 3, 3), O.FLAT, (0.0, 0.0), True, False),
+    # mixed sizes (S1, S2) = (2, 4) / S3 = 3
+    ("mix", (24, 18, 10), (48, 18, 17), (1, 4, 2), O.FLAT, (0.4, 0.3), True, False),
+]
+
+
+@pytest.mark.parametrize("case", FUSED3D_CASES, ids=[c[0] for c in FUSED3D_CASES])
+@pytest.mark.parametrize("T", DTYPES)
+def test_fused_3d_single_pass(li, T, case):
+    """A1*A2*A3 and its adjoint as ONE kernel each (li_sep3d.cuh) against the oracle's three passes, nest order of the
+    reference (A3 first for Direct, A1' first for Adjoint); alpha / beta; a non-finite sample stays in its footprint."""
+    name, m, n, kidx, cond, over, fused_fwd, fused_adj = case
+    rng = np.random.default_rng(abs(hash(name)) % 1000)
+    A, JW = [], []
+    for d in range(3):
+        if over is None:
+            x = 1 + np.arange(n[d]) * 0.98 * (m[d] - 1) / max(n[d] - 1, 1) + (0.37, 0.11, 0.73)[d]
+        else:
+            x = np.linspace(1 - over[0], m[d] + over[1], n[d])
+        ent = KERNELS[kidx[d]]
+        A.append(li.TabulatedInterpolator(T, d + 1, product_kernel(li, ent, cond, T), x, m[d]))
+        JW.append(O.maketable(oracle_kernel(ent, cond), x.astype(T), m[d], T))
+    H = A[0] * A[1] * A[2]
+
+    def oracle_fwd(x, alpha=1, beta=0, dst=None):
+        r = x
+        for d in (2, 1):
+            r = O.tab_direct(JW[d][0], JW[d][1], m[d], d + 1, r)
+        return O.tab_direct(JW[0][0], JW[0][1], m[0], 1, r, alpha, beta, dst)
+
+    def oracle_adj(y, alpha=1, beta=0, dst=None):
+        r = y
+        for d in (0, 1):
+            r = O.tab_adjoint(JW[d][0], JW[d][1], m[d], d + 1, r)
+        return O.tab_adjoint(JW[2][0], JW[2][1], m[2], 3, r, alpha, beta, dst)
+
+    src = np.asfortranarray(rng.standard_normal(m).astype(T))
+    y = np.asfortranarray(rng.standard_normal(n).astype(T))
+    dsrc, dy = li.to_device(src), li.to_device(y)
+    out = H * dsrc
+    back = H.adj * dy
+    assert_close(li.to_host(out), oracle_fwd(src), T)
+    assert_close(li.to_host(back), oracle_adj(y), T)
+    # one launch each once the per-table metadata exists
+    for P, x_in, res, fused in ((li.Direct, dsrc, out, fused_fwd), (li.Adjoint, dy, back, fused_adj)):
+        c0 = li.launch_count()
+        li.apply_b(1, P, H, x_in, False, 0, res)
+        assert (li.launch_count() - c0 == 1) == fused, f"{name}: {li.launch_count() - c0} launches"
+    # alpha, beta
+    d0 = np.asfortranarray(rng.standard_normal(n).astype(T))
+    dd = li.to_device(d0)
+    li.apply_b(0.5, li.Direct, H, dsrc, False, 2, dd)
+    assert_close(li.to_host(dd), oracle_fwd(src, 0.5, 2, d0.copy(order="F")), T)
+    b0 = np.asfortranarray(rng.standard_normal(m).astype(T))
+    db = li.to_device(b0)
+    li.apply_b(-1.5, li.Adjoint, H, dy, False, 0.25, db)
+    assert_close(li.to_host(db), oracle_adj(y, -1.5, 0.25, b0.copy(order="F")), T)
+    # the same numbers as the per-dimension passes of the library (exp bit 2 switches the fused 3-D kernels off)
+    li.set_option("exp", 2)
+    try:
+        out2, back2 = li.to_host(H * dsrc), li.to_host(H.adj * dy)
+    finally:
+        li.set_option("exp", 0)
+    assert_close(out2, oracle_fwd(src), T)
+    assert_close(back2, oracle_adj(y), T)
+    # a NaN / Inf sample reaches exactly the elements it reaches in the reference
+    for bad in (np.nan, np.inf):
+        s2 = src.copy(order="F")
+        s2[m[0] // 2, m[1] // 3, m[2] // 2] = bad
+        s2[0, 0, m[2] - 1] = bad
+        assert np.array_equal(np.isfinite(li.to_host(H * li.to_device(s2))), np.isfinite(np.asarray(oracle_fwd(s2))))
+        y2 = y.copy(order="F")
+        y2[n[0] // 2, n[1] // 3, n[2] // 2] = bad
+        y2[n[0] - 1, 0, 0] = bad
+        assert np.array_equal(np.isfinite(li.to_host(H.adj * li.to_device(y2))), np.isfinite(np.asarray(oracle_adj(y2))))
+
+
 @pytest.mark.parametrize("nframes", [5, 19])   # 19 frames: dealt to concurrent streams with partial accumulators
 def test_sep_apply_batch_accumulates_frames(li, nframes):
     # m += sum_k A_k' y_k in one library call (config #5 in small)
