@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libli_b200.so")
+LIB_PATH = os.environ.get("LI_B200_LIB") or os.path.join(_HERE, "libli_b200.so")   # (override: A/B builds in development)
 
 OK, ERR_ARG, ERR_DIM, ERR_INEXACT, ERR_BOUNDS, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_NCCL = range(9)
 COMM_ID_BYTES = 128

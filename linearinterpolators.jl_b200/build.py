@@ -15,8 +15,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libli_b200.so")
+# development: LI_BUILD_TAG=x builds libli_b200_x.so from build_x/ (A/B builds side by side; load with LI_B200_LIB)
+_TAG = os.environ.get("LI_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "libli_b200" + ("_" + _TAG if _TAG else "") + ".so")
 
 SOURCES = ["li_api.cu", "li_table.cu", "li_tab_apply.cu", "li_sep.cu", "li_sep2d.cu", "li_sep2d_adjs_f32.cu", "li_sep2d_adjs_f64.cu", "li_affine.cu", "li_affine_f32.cu", "li_affine_f64.cu",
            "li_sep2d_multi_f32.cu", "li_sep2d_multi_f64.cu", "li_comm.cu", "li_vec.cu", "li_affine_gather_f32.cu", "li_affine_gather_f64.cu",

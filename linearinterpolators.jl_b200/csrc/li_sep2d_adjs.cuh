@@ -70,7 +70,11 @@ constexpr int ADS3_NC = 4;            // D3: most src planes feeding one dst pla
 // rows land in a second ring (TMA bulk copies, one per plane and row) and every thread combines a few 16-byte vectors
 // of stage j+1 into the row buffer while stage j is consumed.  Only the generic schedule (R = 0) is built.
 template <typename T, int S1, int S2, int NU, int R, bool D3>
-__global__ void __launch_bounds__(ADS_NT, (sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? ADS_PER_SM : ADS_PER_SM / 2)
+#ifndef ADS3_OCC_
+#define ADS3_OCC_ 3
+#endif
+__global__ void __launch_bounds__(ADS_NT, D3 ? ((sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? ADS3_OCC_ : 2)
+                                             : ((sizeof(T) == 4 && NU <= 10 && S2 <= 4) ? ADS_PER_SM : ADS_PER_SM / 2))
 sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 {
     constexpr int NT = ADS_NT, K = AdsK<S2, D3>::value;
@@ -86,8 +90,8 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
     T *sS = reinterpret_cast<T *>(smem_raw);                 // [NSTAGE][K][P1]
     T *sR = sS + (size_t)NSTAGE * K * P1;                    // D3: [NBAR][nc3][K][P1] ring of raw rows
     T *sW2 = sR + (size_t)(D3 ? NBAR * a.nc3 : 0) * K * P1;  // [NRMAX][S2] alpha * folded dim-2 weights
-    int *sNv = reinterpret_cast<int *>(sW2 + (size_t)NRMAX * S2);   // [CR + 2*S2] src rows whose window starts at a dst row
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sNv + ((CR + 2 * S2 + 1) & ~1));   // [NBAR]
+    int *sNv = reinterpret_cast<int *>(sW2 + (size_t)NRMAX * S2);   // [NRMAX] generic loop: dst rows completed before a src row
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sNv + NRMAX);      // [NBAR] (NRMAX is even)
 
     const int tid = threadIdx.x;
     int bid = blockIdx.x;
@@ -223,8 +227,20 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
 
     // chunk metadata: rows per dst row (generic loop only), dim-2 weights
     const int NV = vb - v0;                                   // dst rows v0 .. vb-1
+    // (generic loop: for every src row of the chunk, the number of dst rows its folded window starts after the one of
+    // the previous row -- dst rows that are complete before the row is added; bit 30 marks a window folded at an
+    // edge of the array, where only the slots the clamped taps land on are fed)
+#ifdef ADS_OLD_GENERIC
     if (!regular)
-        for (int k = tid; k < CR + 2 * S2; k += NT) sNv[k] = k < NV ? a.bp2[va + k + 1] - a.bp2[va + k] : 0;
+        for (int k = tid; k < NRMAX; k += NT) sNv[k] = k < NV ? a.bp2[va + k + 1] - a.bp2[va + k] : 0;
+#else
+    if (!regular)
+        for (int k = tid; k < NR; k += NT) {
+            const int b = a.base2[i2lo + k], bf = clampi(b, a.m2 - S2);
+            const int prev = k == 0 ? v0 : clampi(a.base2[i2lo + k - 1], a.m2 - S2);
+            sNv[k] = (bf - prev) | (b != bf ? (1 << 30) : 0);
+        }
+#endif
     for (int k = tid; k < NR * S2; k += NT) sW2[k] = a.alpha * a.W2f[(int64_t)i2lo * S2 + k];
 
     // per-thread dim-1 taps: src columns [e0, e1) feed dst column c; staged window starts at a0 <= e0 (vector aligned)
@@ -401,6 +417,7 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
         }
     };
 
+#ifdef ADS_OLD_GENERIC
     // ---- generic schedule: for dst row vv, every src row whose folded window starts at vv
     auto run_generic = [&](auto clean, auto hasbeta) {
         const T *pw = sW2;
@@ -459,6 +476,74 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
         }
     };
 
+#else
+    // ---- generic schedule: the src rows in order; acc[0] belongs to dst row `vcur`, and the window slides (register
+    // moves) by as many dst rows as the folded window of the next src row starts later -- those rows are complete and
+    // are stored.  Per dst row the contributions arrive in ascending src-row order, as in the reference's scatter.
+    auto run_generic = [&](auto clean, auto hasbeta) {
+        const T *pw = sW2;
+        const int *pa = sNv;
+        int nskip = va - v0;    // leading rows of the window that belong to the previous chunk (or lie before the array)
+        int vcur = v0;
+        T oldq[S2];             // beta != 0: old values of the next S2 rows to be stored, read S2 rows ahead
+        if constexpr (decltype(hasbeta)::value) {
+#pragma unroll
+            for (int i = 0; i < S2; ++i) oldq[i] = oldv[(S2 - 1 + i) % S2];
+        }
+        auto advance = [&]() {   // dst row vcur (slot 0) is complete
+            if (nskip > 0) {
+                --nskip;
+            } else {
+                if constexpr (!decltype(hasbeta)::value) {   // dst is never read
+                    if (have) *dp = acc[0];
+                } else {
+                    const T o = fmaT(betav, oldq[0], acc[0]);
+                    if (have) *dp = o;
+#pragma unroll
+                    for (int i = 0; i + 1 < S2; ++i) oldq[i] = oldq[i + 1];
+                    oldq[S2 - 1] = (T)0;
+                    if (ld_old && vcur + S2 < vb) oldq[S2 - 1] = dp[(int64_t)S2 * dstep];
+                }
+                dp += dstep;
+            }
+#pragma unroll
+            for (int s = 0; s + 1 < S2; ++s) acc[s] = acc[s + 1];
+            acc[S2 - 1] = (T)0;
+            ++vcur;
+        };
+        for (int j = 0; j < NJ; ++j) {
+            const T *prow = next_stage(j);
+            const int nr = min(K, NR - j * K);
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                if (r < nr) {   // block-uniform: only the last stage is partial
+                    const int ad = pa[r];
+#pragma unroll 1
+                    for (int n = ad & 0xffff; n > 0; --n) advance();
+                    const T val = gather(prow, clean);
+                    prow += rowstep;
+                    T w2[S2];
+                    ld_weights<T, S2>(pw, w2);
+                    pw += S2;
+                    if (ad < (1 << 30)) {   // interior window: every slot is fed
+#pragma unroll
+                        for (int s = 0; s < S2; ++s) acc[s] = fmaT(w2[s], val, acc[s]);
+                    } else {                // first / last window of the array: only the slots the clamped taps land on
+                        const int b = a.base2[i2lo + j * K + r];
+                        const int lo = clampi(b, a.m2 - 1) - vcur, hi = clampi(b + S2 - 1, a.m2 - 1) - vcur;
+#pragma unroll
+                        for (int s = 0; s < S2; ++s)
+                            if (s >= lo && s <= hi) acc[s] = fmaT(w2[s], val, acc[s]);
+                    }
+                }
+            }
+            pa += K;
+        }
+#pragma unroll 1
+        while (vcur < vb) advance();   // the last (at most S2) rows of the chunk
+    };
+
+#endif
     // (every copy runs the same sequence of barriers, so warps of one CTA may take different copies)
     auto run = [&](auto hasbeta) {
         if (regular) {
@@ -574,9 +659,13 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     rc = table_chunk_plan(t2, nchunks, 0.3, st, &a.cstart, &CR, &nrmax, &plan);
     if (rc != LI_OK) return rc;
     if (CR > 4096) return LI_OK;
+#ifdef ADS_OLD_GENERIC
+    const int NRMAX = (std::max(std::max(nrmax, 1), CR + 2 * S2) + 1) & ~1;
+#else
     const int NRMAX = (std::max(nrmax, 1) + 1) & ~1;
+#endif
     const size_t smem = (stage_elems * P1 + (size_t)NRMAX * S2) * sizeof(T) +
-                        (size_t)((CR + 2 * S2 + 1) & ~1) * sizeof(int) + NBAR * sizeof(uint64_t);
+                        (size_t)NRMAX * sizeof(int) + NBAR * sizeof(uint64_t);
     if (trace)
         fprintf(stderr, "[li_b200] adj stream%s: NU %d P1 %d CR %d NRMAX %d smem %zu tiles %d x %d x %lld R %d occ %d\n",
                 D3 ? " 3-D" : "", NU, P1, CR, NRMAX, smem, a.tiles1, a.tiles2, (long long)nbatch, R, occ);

@@ -155,12 +155,24 @@ sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, c
     // 16-byte vector at a time; the vectors of an edge strip that hold out-of-range columns read the clamped column
     // instead (the replicated first / last source column)
     const int KP = K * P1;
+    // (the four elements idx .. idx+3 of a row, idx a multiple of 4, into the de-interleaved row buffer: even elements
+    // to the first half of the row, odd ones to the second)
+    auto st_deint = [&](T *out, int r, int c, const Pack<T, 4> &acc) {   // row r, elements c .. c+3 (c % 4 == 0)
+        Pack<T, 2> ev, od;
+        ev.v[0] = acc.v[0], ev.v[1] = acc.v[2], od.v[0] = acc.v[1], od.v[1] = acc.v[3];
+        st_pack<T, 2>(out + r * P1 + (c >> 1), ev);
+        st_pack<T, 2>(out + r * P1 + (c >> 1) + (P1 >> 1), od);
+    };
+    const int nv1 = P1 >> 2;                                 // vectors per staged row
+    const int vr0 = tid / nv1, vc0 = tid - vr0 * nv1;        // this thread's first vector (row, vector in the row)
+    const int dvr = NT / nv1, dvc = NT - dvr * nv1;          // ... and the step to its next one
     auto combine_nc = [&](int j, auto NCt) {
         constexpr int NC = decltype(NCt)::value;
         const T *raw = sR + (size_t)(j % NBAR) * NC * KP;
         T *out = sS + (size_t)(j % NSTAGE) * KP;
-        if (!patch) {
-            for (int idx = 4 * tid; idx < KP; idx += 4 * NT) {
+        for (int r = vr0, c = vc0; r < K;) {
+            const int c4 = 4 * c, idx = r * P1 + c4;
+            if (!patch || (c4 >= cv0 && c4 + 4 <= cv1)) {
                 Pack<T, 4> acc = ld_pack<T, 4>(raw + idx);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc.v[e] *= w3[0];
@@ -170,33 +182,18 @@ sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, c
 #pragma unroll
                     for (int e = 0; e < 4; ++e) acc.v[e] = fmaT(w3[t], q.v[e], acc.v[e]);
                 }
-                st_pack<T, 4>(out + idx, acc);
-            }
-        } else {
-            const int nv1 = P1 >> 2;                         // vectors per staged row
-            for (int v = tid; v < K * nv1; v += NT) {
-                const int r = v / nv1, c4 = 4 * (v - r * nv1), idx = 4 * v;
-                if (c4 >= cv0 && c4 + 4 <= cv1) {
-                    Pack<T, 4> acc = ld_pack<T, 4>(raw + idx);
+                st_deint(out, r, c4, acc);
+            } else {   // (edge strips: a few vectors per row)
+                for (int e = 0; e < 4; ++e) {
+                    const int cs = r * P1 + min(max(c4 + e, cv0), cv1 - 1);
+                    T acc = raw[cs] * w3[0];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) acc.v[e] *= w3[0];
-#pragma unroll
-                    for (int t = 1; t < NC; ++t) {
-                        const Pack<T, 4> q = ld_pack<T, 4>(raw + t * KP + idx);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) acc.v[e] = fmaT(w3[t], q.v[e], acc.v[e]);
-                    }
-                    st_pack<T, 4>(out + idx, acc);
-                } else {
-                    for (int e = 0; e < 4; ++e) {
-                        const int cs = r * P1 + min(max(c4 + e, cv0), cv1 - 1);
-                        T acc = raw[cs] * w3[0];
-#pragma unroll
-                        for (int t = 1; t < NC; ++t) acc = fmaT(w3[t], raw[t * KP + cs], acc);
-                        out[idx + e] = acc;
-                    }
+                    for (int t = 1; t < NC; ++t) acc = fmaT(w3[t], raw[t * KP + cs], acc);
+                    out[r * P1 + ((c4 + e) >> 1) + ((c4 + e) & 1) * (P1 >> 1)] = acc;
                 }
             }
+            r += dvr, c += dvc;
+            if (c >= nv1) c -= nv1, ++r;
         }
     };
     auto combine = [&](int j) {
@@ -241,6 +238,12 @@ sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, c
         w1B[s] = a.W1[(int64_t)iB * S1 + s];
     }
     const bool shift = offB != offA;   // PAIR: offB - offA is 0 or 1
+    // D3: the row buffers are de-interleaved -- element e of a staged row sits at (e >> 1) + (e & 1) * P1/2 -- so that
+    // lanes whose windows start two elements apart (a unit-rate table: two output columns per thread) read consecutive
+    // words.  posX0 / posX1: where the elements offX and offX + 1 sit; tap s reads posX{s & 1}[s >> 1].
+    const int H1 = P1 >> 1;
+    const int posA0 = (offA >> 1) + (offA & 1) * H1, posA1 = ((offA + 1) >> 1) + ((offA + 1) & 1) * H1;
+    const int posB0 = (offB >> 1) + (offB & 1) * H1, posB1 = ((offB + 1) >> 1) + ((offB + 1) & 1) * H1;
     const bool vec = a.vec_ok && haveB;
     const T *wp = sW2;                                  // weights of the next output row
     T *dp = dst + (int64_t)i2a * a.n1 + colA;           // next output element
@@ -284,10 +287,16 @@ sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, c
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             if constexpr (PAIR) {
-                const T *p = buf + u * P1 + offA;
                 T v[S1 + 1];
+                if constexpr (D3) {   // de-interleaved row buffer (see combine): conflict-free for unit-rate tables too
+                    const T *pe = buf + u * P1 + posA0, *po = buf + u * P1 + posA1;
 #pragma unroll
-                for (int s = 0; s <= S1; ++s) v[s] = p[s];
+                    for (int s = 0; s <= S1; ++s) v[s] = (s & 1) ? po[s >> 1] : pe[s >> 1];
+                } else {
+                    const T *p = buf + u * P1 + offA;
+#pragma unroll
+                    for (int s = 0; s <= S1; ++s) v[s] = p[s];
+                }
                 T accA = v[0] * w1A[0];
                 T accB = (shift ? v[1] : v[0]) * w1B[0];
 #pragma unroll
@@ -297,13 +306,26 @@ sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, c
                 }
                 nA[u] = accA, nB[u] = accB;
             } else {
-                const T *p = buf + u * P1 + offA, *q = buf + u * P1 + offB;
-                T accA = p[0] * w1A[0];
-                T accB = q[0] * w1B[0];
+                T accA, accB;
+                if constexpr (D3) {
+                    const T *pe = buf + u * P1 + posA0, *po = buf + u * P1 + posA1;
+                    const T *qe = buf + u * P1 + posB0, *qo = buf + u * P1 + posB1;
+                    accA = pe[0] * w1A[0];
+                    accB = qe[0] * w1B[0];
 #pragma unroll
-                for (int s = 1; s < S1; ++s) {
-                    accA = fmaT(p[s], w1A[s], accA);
-                    accB = fmaT(q[s], w1B[s], accB);
+                    for (int s = 1; s < S1; ++s) {
+                        accA = fmaT((s & 1) ? po[s >> 1] : pe[s >> 1], w1A[s], accA);
+                        accB = fmaT((s & 1) ? qo[s >> 1] : qe[s >> 1], w1B[s], accB);
+                    }
+                } else {
+                    const T *p = buf + u * P1 + offA, *q = buf + u * P1 + offB;
+                    accA = p[0] * w1A[0];
+                    accB = q[0] * w1B[0];
+#pragma unroll
+                    for (int s = 1; s < S1; ++s) {
+                        accA = fmaT(p[s], w1A[s], accA);
+                        accB = fmaT(q[s], w1B[s], accB);
+                    }
                 }
                 nA[u] = accA, nB[u] = accB;
             }
