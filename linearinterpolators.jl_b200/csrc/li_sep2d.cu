@@ -561,6 +561,13 @@ static int launch_adj(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     return LI_OK;
 }
 
+#define LI_MORE_DECL(NAME)                                                                                          \
+    template <typename T>                                                                                           \
+    int NAME(int adjoint, SepArgs<T> &a, const li_table *t1, const li_table *t2, int64_t nbatch, cudaStream_t st,   \
+             bool *done, bool *mine);
+LI_MORE_DECL(sep2d_more_a) LI_MORE_DECL(sep2d_more_b) LI_MORE_DECL(sep2d_more_c) LI_MORE_DECL(sep2d_more_d)
+#undef LI_MORE_DECL
+
 template <typename T>
 static int fused_T(int adjoint, const li_table *t1, const li_table *t2, int64_t nbatch, double alpha,
                    const void *src, double beta, void *dst, cudaStream_t st, bool *done)
@@ -580,7 +587,15 @@ static int fused_T(int adjoint, const li_table *t1, const li_table *t2, int64_t 
     LI_SEP(2, 2) LI_SEP(4, 4) LI_SEP(6, 6) LI_SEP(2, 4) LI_SEP(4, 2) LI_SEP(4, 6) LI_SEP(6, 4) LI_SEP(3, 3)
     LI_SEP(2, 1) LI_SEP(3, 1) LI_SEP(4, 1) LI_SEP(6, 1)   // (second factor = identity: 1-D applies along dim 1)
 #undef LI_SEP
-    return LI_OK;   // size pair not built: decline
+    // the other pairs of {2, 3, 4, 6, 8}^2: streaming kernels only (li_sep2d_more.cuh)
+    bool mine = false;
+    int rc = sep2d_more_a<T>(adjoint, a, t1, t2, nbatch, st, done, &mine);
+    if (!mine) rc = sep2d_more_b<T>(adjoint, a, t1, t2, nbatch, st, done, &mine);
+    if (!mine) rc = sep2d_more_c<T>(adjoint, a, t1, t2, nbatch, st, done, &mine);
+    if (!mine) rc = sep2d_more_d<T>(adjoint, a, t1, t2, nbatch, st, done, &mine);
+    if (!mine && opt(OPT_TRACE))
+        fprintf(stderr, "[li_b200] fused 2-D: no kernel for the size pair (%d, %d): per-dimension passes\n", S1, S2);
+    return rc;
 }
 
 int sep2d_fused_supported(const li_table *t1, const li_table *t2)

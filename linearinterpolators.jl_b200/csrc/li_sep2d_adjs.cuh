@@ -56,7 +56,8 @@ constexpr int ADS_PER_SM = ADS_OCC_ * 256 / ADS_NT;   // CTAs per SM of the 4-by
 
 template <int S2, bool D3 = false>
 struct AdsK {   // src rows per stage: a multiple of 2*S2 so that the static schedule has whole slot rotations
-    static constexpr int value = D3 ? ((S2 == 6 || S2 == 3) ? 6 : 4) : ((S2 == 6 || S2 == 3) ? 12 : ADS_K_);
+    static constexpr int value = D3 ? ((S2 == 6 || S2 == 3) ? 6 : (S2 == 8 ? 8 : 4))
+                                    : ((S2 == 6 || S2 == 3) ? 12 : (S2 == 8 ? 16 : ADS_K_));
 };
 #ifndef ADS3_NSR_
 #define ADS3_NSR_ 2

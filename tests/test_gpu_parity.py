@@ -631,6 +631,38 @@ def test_separable_3d_passes(li):
     assert_close(li.to_host(H.adj * li.to_device(y)), refa, T, factor=64)
 
 
+# one kernel family per size S = 2, 3, 4, 6, 8
+_BY_SIZE = {2: KERNELS[1], 3: KERNELS[2], 4: KERNELS[4], 6: KERNELS[9], 8: KERNELS[10]}
+
+
+@pytest.mark.parametrize("S2", [2, 3, 4, 6, 8])
+@pytest.mark.parametrize("S1", [2, 3, 4, 6, 8])
+def test_fused_2d_every_size_pair(li, S1, S2):
+    """Every pair of kernel sizes of {2, 3, 4, 6, 8}^2 runs as ONE fused kernel per apply (no silent fall back to the
+    per-dimension passes), Direct and Adjoint, an up-sampling and a non-integer rate, against the oracle."""
+    T = np.float32
+    rng = np.random.default_rng(100 * S1 + S2)
+    e1, e2 = _BY_SIZE[S1], _BY_SIZE[S2]
+    for (m1, m2, n1, n2) in ((48, 40, 96, 80), (64, 36, 88, 52)):
+        x1 = np.linspace(0.25, m1 + 0.5, n1)
+        x2 = np.linspace(-0.5, m2 + 1.25, n2)
+        A1 = li.TabulatedInterpolator(T, 1, product_kernel(li, e1, O.FLAT, T), x1, m1)
+        A2 = li.TabulatedInterpolator(T, 2, product_kernel(li, e2, O.SAFEFLAT, T), x2, m2)
+        J1, W1 = O.maketable(oracle_kernel(e1, O.FLAT), x1.astype(T), m1, T)
+        J2, W2 = O.maketable(oracle_kernel(e2, O.SAFEFLAT), x2.astype(T), m2, T)
+        H = A1 * A2
+        src = np.asfortranarray(rng.standard_normal((m1, m2)).astype(T))
+        y = np.asfortranarray(rng.standard_normal((n1, n2)).astype(T))
+        dsrc, dy = li.to_device(src), li.to_device(y)
+        out, back = H * dsrc, H.adj * dy
+        assert_close(li.to_host(out), O.tab_direct(J1, W1, m1, 1, O.tab_direct(J2, W2, m2, 2, src)), T)
+        assert_close(li.to_host(back), O.tab_adjoint(J2, W2, m2, 2, O.tab_adjoint(J1, W1, m1, 1, y)), T)
+        for P, x_in, res in ((li.Direct, dsrc, out), (li.Adjoint, dy, back)):
+            c0 = li.launch_count()
+            li.apply_b(1, P, H, x_in, False, 0, res)
+            assert li.launch_count() - c0 == 1, f"({S1}, {S2}) {P}: {li.launch_count() - c0} launches"
+
+
 # (name, m, n, kernel entries per dim, condition, position range per dim as (first, last) in units of the source grid,
 #  fused forward expected, fused adjoint expected)
 FUSED3D_CASES = [
