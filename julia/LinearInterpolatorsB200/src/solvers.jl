@@ -32,7 +32,7 @@ function allreduce_sum!(comm::Comm, x::DeviceArray{T}) where {T<:Floats}
 end
 
 """
-    adjoint_accumulate!(model, ops, ys; α=1, β=0, comm=nothing, nbands=4)
+    adjoint_accumulate!(model, ops, ys; α=1, β=0, comm=nothing, nbands=1)
 
 `model <- β*model + α * Σ_ranks Σ_k H_k' * ys[k]` with `H_k = ops[k] = (A1_k, A2_k)` the per-dimension operators of
 local frame `k`: the multi-frame accumulate kernel on this GPU, band by band, the NCCL all-reduce of a band
@@ -40,7 +40,7 @@ overlapping the next band (`li_adjoint_accumulate_allreduce`).  Replaces the ref
 `for k: apply!(1, Adjoint, H_k, y_k, false, 1, model)` (src/tabulated.jl:441-478 per factor).
 """
 function adjoint_accumulate!(model::DeviceArray{T,2}, ops::AbstractVector, ys::AbstractVector{<:DeviceArray{T,2}};
-                             α::Real=1, β::Real=0, comm::Union{Nothing,Comm}=nothing, nbands::Integer=4) where {T<:Floats}
+                             α::Real=1, β::Real=0, comm::Union{Nothing,Comm}=nothing, nbands::Integer=1) where {T<:Floats}
     n = length(ops)
     n == length(ys) || throw(DimensionMismatch("one frame per operator"))
     handles = Ptr{Cvoid}[f.table.handle for op in ops for f in op]

@@ -20,7 +20,8 @@ from .separable import sep2d_otf_apply, sep_apply_batch, sep_apply_tables
 from .sparse import Range, SparseInterpolator, SparseUnidimensionalInterpolator, fractional_index
 from .tabulated import TabulatedInterpolator, coefficients, columns, ncols, nrows, width
 from .unidimensional import otf1d_apply
-from .distributed import Comm, FrameBatch, accumulate_adjoint, adjoint_accumulate, shard_range, world_info
+from .distributed import (Comm, FrameBatch, accumulate_adjoint, adjoint_accumulate, bind_host_to_device, shard_range,
+                          world_info)
 from .solvers import CgResult, conjgrad, fit_separable, vcombine, vdot_device, vupdate
 
 

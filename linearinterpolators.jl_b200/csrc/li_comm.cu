@@ -139,7 +139,11 @@ namespace li {
 
 static int comm_finish_init(li_comm *c)
 {
-    LI_CUDA(cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
+    // highest priority: the all-reduce of a finished band must get its few CTAs scheduled ahead of the queued CTAs of
+    // the next band's compute kernel, not behind them
+    int prio_lo = 0, prio_hi = 0;
+    LI_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    LI_CUDA(cudaStreamCreateWithPriority(&c->cs, cudaStreamNonBlocking, prio_hi));
     for (int b = 0; b < li_comm::MAXB; ++b) LI_CUDA(cudaEventCreateWithFlags(&c->ev_band[b], cudaEventDisableTiming));
     LI_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
     return LI_OK;

@@ -20,6 +20,39 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + q + (1 if rank < r else 0)
 
 
+def bind_host_to_device(device_index: int) -> dict:
+    """Pins the calling process to the CPU cores NVML reports as local to GPU ``device_index`` (its NUMA node), so that
+    pinned host buffers allocated afterwards are first-touched on that node and the host-buffer entry points
+    (``li_*_host``) do not cross the inter-socket link: with one process per GPU on a two-socket box, eight ranks that
+    all stage through one node's memory share its bandwidth.  Returns what was done (for the bench line); never raises.
+    """
+    import os
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # CUDA_VISIBLE_DEVICES renumbers devices: go through the PCI bus id of the CUDA device
+        handle = None
+        try:
+            import torch
+            bus = torch.cuda.get_device_properties(device_index)
+            pci = f"{getattr(bus, 'pci_domain_id', 0):08x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(pci.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info = {"bound": True, "cpus": len(cpus), "first_cpu": min(cpus), "allowed_before": len(allowed)}
+    except Exception as exc:  # pragma: no cover - depends on the box
+        info["why"] = f"{type(exc).__name__}: {exc}"[:120]
+    return info
+
+
 def world_info():
     """(rank, world) of the default process group, (0, 1) when torch.distributed is not initialised."""
     try:
@@ -201,7 +234,7 @@ class FrameBatch:
         return self.n
 
 
-def adjoint_accumulate(tabs_list, srcs=None, model=None, alpha=1.0, beta=0.0, comm: Optional[Comm] = None, nbands: int = 4):
+def adjoint_accumulate(tabs_list, srcs=None, model=None, alpha=1.0, beta=0.0, comm: Optional[Comm] = None, nbands: int = 1):
     """``model <- beta*model + alpha * sum over all ranks and local frames k of (A1_k*A2_k)' * y_k`` in one library
     call (``li_adjoint_accumulate_allreduce``): the multi-frame accumulate kernel on the local frames, band by band,
     with the NCCL all-reduce of each band overlapping the next band's computation.  ``tabs_list[k]`` = the two
