@@ -67,6 +67,10 @@ typedef enum {
     LI_MITCHELLNETRAVALI = 7, /* MitchellNetravaliSpline(b, c), S = 4, params[0..1] */
     LI_LANCZOS = 8            /* LanczosKernel(S), S even, 2 <= S <= 16 */
 } li_family;
+/* family | LI_PRIME: the derivative kernel (RectangularSplinePrime ... LanczosKernelPrime,
+ * src/LinearInterpolators.jl:23-41): getweights yields d/dt of the weights of the base kernel, everything else
+ * (window, Flat / SafeFlat clamping of src/boundaries.jl:77-156, which does not look at the kernel) is unchanged. */
+#define LI_PRIME 16
 
 /* Boundary tag B of Kernel{T,S,B}; selects FlatLimits / SafeFlatLimits
  * (src/types.jl:27-52, src/boundaries.jl:37-42). */
@@ -291,6 +295,14 @@ LI_API int li_conjgrad(li_apply_fn A, void *ctx, int dtype, int64_t n, const voi
 LI_API int li_conjgrad_sep(int ndim, const li_table *const *tabs, const int64_t *dims_other, int64_t nbatch, double mu,
                            const void *y_dev, void *x_dev, int x_is_zero, const li_cg_options *opts, li_cg_info *info,
                            void *stream);
+
+/* ---- normal equations (src/sparse.jl:277-356, 424-490) ------------------------
+ * li_table_atwa: dst[ncols, ncols] (column-major, device) <- A'*diag(w)*A, w[nrows] device weights or NULL for A'*A
+ * (AtA! / AtWA!).  Every element is summed by one thread in the reference's (row, tap, tap) order: deterministic.
+ * li_regularize: A <- A + rho*(eps*I + mu*D'*D), rho the largest diagonal element, D first-order differences
+ * (regularize!); synchronises the stream to check rho > 0 (LI_ERR_ARG "we have a problem!" otherwise, as the reference). */
+LI_API int li_table_atwa(const li_table *t, const void *w_dev, void *dst_dev, void *stream);
+LI_API int li_regularize(int dtype, void *A_dev, int64_t n, double eps, double mu, void *stream);
 
 /* ---- dispatch switches ------------------------------------------------------
  * Process-wide integer options, initialised once from the environment at load time (LI_B200_<NAME>): "no_fused",

@@ -8,7 +8,8 @@ module LinearInterpolatorsB200
 
 export TabulatedInterpolator, SparseInterpolator, SparseUnidimensionalInterpolator,
     TwoDimensionalTransformInterpolator, DeviceArray, Comm, comm_unique_id, allreduce_sum!, adjoint_accumulate!,
-    fit_separable, sep_apply!, sep_accumulate!, rows, columns, nrows, ncols, width, convert_coordinate
+    fit_separable, sep_apply!, sep_accumulate!, rows, columns, nrows, ncols, width, convert_coordinate, AtA, AtWA,
+    regularize, regularize!
 
 using InterpolationKernels
 using TwoDimensional: AffineTransform2D

@@ -11,11 +11,26 @@ family_code(::CardinalCubicSpline) = Int32(5)
 family_code(::KeysSpline) = Int32(6)
 family_code(::MitchellNetravaliSpline) = Int32(7)
 family_code(::LanczosKernel) = Int32(8)
+# the derivative kernels (src/LinearInterpolators.jl:23-41): LI_PRIME = 16 or-ed into the family of the base kernel; the
+# library then evaluates d/dt of the base weights (li_weights.cuh: getweights_prime)
+const LI_PRIME = Int32(16)
+family_code(::RectangularSplinePrime) = Int32(0) | LI_PRIME
+family_code(::LinearSplinePrime) = Int32(1) | LI_PRIME
+family_code(::QuadraticSplinePrime) = Int32(2) | LI_PRIME
+family_code(::CubicSplinePrime) = Int32(3) | LI_PRIME
+family_code(::CatmullRomSplinePrime) = Int32(4) | LI_PRIME
+family_code(::CardinalCubicSplinePrime) = Int32(5) | LI_PRIME
+family_code(::KeysSplinePrime) = Int32(6) | LI_PRIME
+family_code(::MitchellNetravaliSplinePrime) = Int32(7) | LI_PRIME
+family_code(::LanczosKernelPrime) = Int32(8) | LI_PRIME
 
 family_params(::Kernel) = (0.0, 0.0, 0.0, 0.0)
 family_params(k::CardinalCubicSpline) = (Float64(k.c), 0.0, 0.0, 0.0)
 family_params(k::KeysSpline) = (Float64(k.a), 0.0, 0.0, 0.0)
 family_params(k::MitchellNetravaliSpline) = (Float64(k.b), Float64(k.c), 0.0, 0.0)
+family_params(k::CardinalCubicSplinePrime) = (Float64(k.c), 0.0, 0.0, 0.0)
+family_params(k::KeysSplinePrime) = (Float64(k.a), 0.0, 0.0, 0.0)
+family_params(k::MitchellNetravaliSplinePrime) = (Float64(k.b), Float64(k.c), 0.0, 0.0)
 
 boundary_code(::Kernel{T,S,Flat}) where {T,S} = Int32(0)
 boundary_code(::Kernel{T,S,SafeFlat}) where {T,S} = Int32(1)

@@ -48,6 +48,44 @@ import SparseArrays
 SparseArrays.sparse(A::Union{AbstractSparseInterpolator,TabulatedInterpolator}) =
     SparseArrays.sparse(rows(A), vec(columns(A)), vec(coefficients(A)), nrows(A), ncols(A))   # src/sparse.jl:88-89
 
+# ---- normal equations of a 1-D fit (src/sparse.jl:277-490): dense ncols x ncols matrices built on the device
+const RGL_EPS = 1e-9
+const RGL_MU = 0.0
+
+"""
+    AtA(A) / AtWA(A, w)
+
+yield `A'*A` / `A'*diag(w)*A` (reference `AtA`, `AtWA`, src/sparse.jl:277-356) as a host matrix; a `DeviceArray` of
+weights gives a `DeviceArray` (`li_table_atwa`: every element summed by one thread in the reference's order).
+"""
+AtA(A::SparseInterpolator{T}) where {T} = Array(_atwa(A, nothing))
+AtWA(A::SparseInterpolator{T,S,N}, w::AbstractArray{T,N}) where {T,S,N} = Array(_atwa(A, DeviceArray(Array(w))))
+AtWA(A::SparseInterpolator{T,S,N}, w::DeviceArray{T,N}) where {T,S,N} = _atwa(A, w)
+function _atwa(A::SparseInterpolator{T}, w) where {T}
+    w === nothing || size(w) == output_size(A) || throw(AssertionError("size(wgt) == output_size(A)"))
+    dst = DeviceArray{T}(undef, (A.ncols, A.ncols))
+    GC.@preserve A w dst check(ccall((:li_table_atwa, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                                     A.table.handle, w === nothing ? C_NULL : w.ptr, dst.ptr, C_NULL))
+    check(ccall((:li_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+    return dst
+end
+
+"""
+    regularize!(A, ϵ=1e-9, μ=0) / regularize(A, ϵ, μ)
+
+`A + ρ*(ϵ*I + μ*D'*D)`, `ρ` the largest diagonal element (src/sparse.jl:424-490), in place on a `DeviceArray`
+(`li_regularize`) or through the device for a host matrix.
+"""
+function regularize!(A::DeviceArray{T,2}, eps::Real=RGL_EPS, mu::Real=RGL_MU) where {T<:Floats}
+    size(A, 1) == size(A, 2) || throw(AssertionError("size(A,1) == size(A,2)"))
+    (eps ≥ 0 && mu ≥ 0) || throw(AssertionError("eps ≥ 0 && mu ≥ 0"))
+    check(ccall((:li_regularize, LIB), Cint, (Cint, Ptr{Cvoid}, Int64, Cdouble, Cdouble, Ptr{Cvoid}),
+                li_dtype(T), A.ptr, size(A, 1), eps, mu, C_NULL))
+    return A
+end
+regularize!(A::Matrix{T}, args...) where {T<:Floats} = copyto!(A, Array(regularize!(DeviceArray(A), args...)))
+regularize(A::AbstractMatrix{T}, args...) where {T<:Floats} = regularize!(copyto!(Array{T}(undef, size(A)), A), args...)
+
 SparseInterpolator(ker::Kernel{T}, args...) where {T<:AbstractFloat} = SparseInterpolator{T}(ker, args...)
 SparseInterpolator{T}(ker::Kernel, args...) where {T<:AbstractFloat} = SparseInterpolator{T}(T(ker), args...)
 SparseInterpolator{T}(ker::Kernel{T,S}, pos::AbstractArray{<:Real,N}, grd::AbstractRange) where {T<:Floats,S,N} =

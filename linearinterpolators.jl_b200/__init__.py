@@ -10,14 +10,17 @@ from . import _lib
 from ._arrays import DeviceArray, HostStream, async_host, device_empty, pinned_empty, to_device, to_host
 from ._lib import (ArgumentError, CudaError, DimensionMismatch, ErrorException, InexactError, LIB_PATH,
                    VARIANT_ATOMIC, VARIANT_AUTO, VARIANT_GATHER, get_option, launch_count, set_option)
-from .kernels import (Boundaries, CardinalCubicSpline, CatmullRomSpline, CubicSpline, Flat, Kernel, KeysSpline,
-                      LanczosKernel, LinearSpline, MitchellNetravaliSpline, QuadraticSpline, RectangularSpline,
-                      SafeFlat, boundaries)
+from .kernels import (Boundaries, CardinalCubicSpline, CardinalCubicSplinePrime, CatmullRomSpline, CatmullRomSplinePrime,
+                      CubicSpline, CubicSplinePrime, Flat, Kernel, KeysSpline, KeysSplinePrime, LanczosKernel,
+                      LanczosKernelPrime, LinearSpline, LinearSplinePrime, MitchellNetravaliSpline,
+                      MitchellNetravaliSplinePrime, QuadraticSpline, QuadraticSplinePrime, RectangularSpline,
+                      RectangularSplinePrime, SafeFlat, boundaries, iscardinal, isnormalized)
 from .mapping import (Adjoint, AdjointMapping, Composition, Direct, Gram, LinearMapping, Mapping, Operations,
                       Table, apply, apply_, apply_b, vcreate, vdot)
 from .nonseparable import AffineTransform2D, TwoDimensionalTransformInterpolator, affine_apply, intercept, rotate
 from .separable import sep2d_otf_apply, sep_apply_batch, sep_apply_tables
-from .sparse import Range, SparseInterpolator, SparseUnidimensionalInterpolator, fractional_index
+from .sparse import (AtA, AtWA, Range, SparseInterpolator, SparseUnidimensionalInterpolator, fit, fractional_index,
+                     regularize, regularize_)
 from .tabulated import TabulatedInterpolator, coefficients, columns, ncols, nrows, width
 from .unidimensional import otf1d_apply
 from .distributed import (Comm, FrameBatch, accumulate_adjoint, adjoint_accumulate, bind_host_to_device, shard_range,

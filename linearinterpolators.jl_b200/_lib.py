@@ -19,6 +19,7 @@ FLAT, SAFEFLAT = 0, 1
 VARIANT_AUTO, VARIANT_GATHER, VARIANT_ATOMIC = 0, 1, 2
 FLAG_ASYNC = 1
 MAX_S = 16
+PRIME = 16          # LI_PRIME: family | PRIME = the derivative kernel
 
 
 class KernelDesc(C.Structure):
@@ -137,6 +138,8 @@ _PROTOS = {
     "li_allreduce_sum": (_int, [_vp, _int, _vp, _i64, _vp]),
     "li_adjoint_accumulate_allreduce": (_int, [_vp, _int, _i64, _i64, _i64, C.POINTER(_vp), C.POINTER(_vp), _dbl, _dbl, _vp,
                                                _int, _vp]),
+    "li_table_atwa": (_int, [_vp, _vp, _vp, _vp]),
+    "li_regularize": (_int, [_int, _vp, _i64, _dbl, _dbl, _vp]),
     "li_vdot": (_int, [_int, _vp, _vp, _i64, C.POINTER(_dbl), _vp]),
     "li_vdot_async": (_int, [_int, _vp, _vp, _i64, _vp, _vp]),
     "li_vupdate": (_int, [_int, _vp, _dbl, _vp, _i64, _vp]),

@@ -23,7 +23,7 @@ LIB = os.path.join(HERE, "libli_b200" + ("_" + _TAG if _TAG else "") + ".so")
 SOURCES = ["li_api.cu", "li_table.cu", "li_tab_apply.cu", "li_sep.cu", "li_sep2d.cu", "li_sep2d_adjs_f32.cu", "li_sep2d_adjs_f64.cu", "li_affine.cu", "li_affine_f32.cu", "li_affine_f64.cu",
            "li_sep2d_multi_f32.cu", "li_sep2d_multi_f64.cu", "li_comm.cu", "li_vec.cu", "li_affine_gather_f32.cu", "li_affine_gather_f64.cu",
            "li_sep3d_f32.cu", "li_sep3d_f64.cu", "li_sep2d_more_a.cu", "li_sep2d_more_b.cu", "li_sep2d_more_c.cu",
-           "li_sep2d_more_d.cu"]
+           "li_sep2d_more_d.cu", "li_normal.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

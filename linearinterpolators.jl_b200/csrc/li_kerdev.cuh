@@ -35,18 +35,20 @@ int make_kerdev(const li_kernel_desc *d, int64_t len, KerDev<T> *k)
     LI_REQUIRE(d->boundary == LI_FLAT || d->boundary == LI_SAFEFLAT, LI_ERR_ARG, "unknown boundary conditions");
     LI_REQUIRE(len >= 1, LI_ERR_ARG, "dimension length must be at least 1");  // src/types.jl:30,49
     const int S = d->S;
-    if (d->family == LI_LANCZOS) {
+    const int family = d->family & ~LI_PRIME;
+    if (family == LI_LANCZOS) {
         LI_REQUIRE(S >= 2 && S <= LI_MAX_S && (S & 1) == 0, LI_ERR_UNSUPPORTED,
                    "LanczosKernel size must be even and in 2:%d (got %d)", LI_MAX_S, S);
     } else {
-        LI_REQUIRE(expected_size(d->family) == S, LI_ERR_ARG, "kernel family %d cannot have size %d", d->family, S);
+        LI_REQUIRE(expected_size(family) == S, LI_ERR_ARG, "kernel family %d cannot have size %d", family, S);
     }
     memset(k, 0, sizeof *k);
-    k->family = d->family;
+    k->family = family;
+    k->deriv = (d->family & LI_PRIME) ? 1 : 0;
     k->S = S;
     k->boundary = d->boundary;
     const double pi = 3.14159265358979323846;
-    switch (d->family) {
+    switch (family) {
     case LI_QUADRATIC:
         k->c[0] = (T)0.35355339059327376220042218105242451964241796884424;
         k->c[1] = (T)0.70710678118654752440084436210484903928483593768847;

@@ -184,15 +184,170 @@ __device__ inline float li_sin(float x)
     }
 }
 
+// cos(): same reduction as li_sin, the kernels of the next quadrant (msun s_cos.c / s_cosf.c), without FMA.
+__device__ inline double li_cos(double x)
+{
+    const double INVPIO2 = __longlong_as_double(0x3FE45F306DC9C883ull);
+    const double PIO2_1 = __longlong_as_double(0x3FF921FB54400000ull);
+    const double PIO2_1T = __longlong_as_double(0x3DD0B4611A626331ull);
+    const double PIO2_2 = __longlong_as_double(0x3DD0B4611A600000ull);
+    const double PIO2_2T = __longlong_as_double(0x3BA3198A2E037073ull);
+    const double PIO2_3 = __longlong_as_double(0x3BA3198A2E000000ull);
+    const double PIO2_3T = __longlong_as_double(0x397B839A252049C1ull);
+    double ax = fabs(x);
+    if (ax < 0.78539816339744830962) return msun_kcos(x, 0.0);
+    if (!(ax < CUDART_INF)) return dsub(x, x);
+    double fn = rint(dmul(x, INVPIO2));
+    int n = (int)fn;
+    double r = dsub(x, dmul(fn, PIO2_1));
+    double w = dmul(fn, PIO2_1T);
+    int ex = msun_exponent(x);
+    double y = dsub(r, w);
+    if (ex - msun_exponent(y) > 16) {
+        double t = r;
+        w = dmul(fn, PIO2_2);
+        r = dsub(t, w);
+        w = dsub(dmul(fn, PIO2_2T), dsub(dsub(t, r), w));
+        y = dsub(r, w);
+        if (ex - msun_exponent(y) > 49) {
+            t = r;
+            w = dmul(fn, PIO2_3);
+            r = dsub(t, w);
+            w = dsub(dmul(fn, PIO2_3T), dsub(dsub(t, r), w));
+            y = dsub(r, w);
+        }
+    }
+    double y1 = dsub(dsub(r, y), w);
+    switch (n & 3) {
+    case 0:
+        return msun_kcos(y, y1);
+    case 1:
+        return -msun_ksin(y, y1, true);
+    case 2:
+        return -msun_kcos(y, y1);
+    default:
+        return msun_ksin(y, y1, true);
+    }
+}
+
+__device__ inline float li_cos(float x)
+{
+    const double INVPIO2 = __longlong_as_double(0x3FE45F306DC9C883ull);
+    const double PIO2_1 = __longlong_as_double(0x3FF921FB50000000ull);
+    const double PIO2_1T = __longlong_as_double(0x3E5110B4611A6263ull);
+    float ax = fabsf(x);
+    if (ax < 0.78539818525314331f) return msun_kcosdf((double)x);
+    if (!(ax < CUDART_INF_F)) return __fsub_rn(x, x);
+    double xd = (double)x;
+    double fn = rint(dmul(xd, INVPIO2));
+    int n = (int)fn & 3;
+    double y = dsub(dsub(xd, dmul(fn, PIO2_1)), dmul(fn, PIO2_1T));
+    switch (n) {
+    case 0:
+        return msun_kcosdf(y);
+    case 1:
+        return -msun_ksindf(y);
+    case 2:
+        return -msun_kcosdf(y);
+    default:
+        return msun_ksindf(y);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Kernel description as the device sees it: every constant already rounded to T
 // on the host (InterpolationKernels stores its constants as T fields).
 template <typename T>
 struct KerDev {
-    int32_t family, S, boundary, pad;
+    int32_t family, S, boundary, deriv;   // deriv != 0: the derivative kernel (LI_PRIME)
     T c[8];      // family-specific constants
     T inf, sup;  // SafeFlatLimits (src/boundaries.jl:40-42)
 };
+
+// getweights(ker', t): the derivative kernels (`*Prime` of InterpolationKernels 0.1.x, re-exported at
+// src/LinearInterpolators.jl:23-41): w'_s(t) = d/dt w_s(t), the weights being w_s(t) = ker(t - s + const).
+template <typename T, int S>
+__device__ __forceinline__ void getweights_prime(const KerDev<T> &k, T t, T (&w)[S])
+{
+    using A = Ar<T>;
+    const T one = (T)1, two = (T)2, half = (T)0.5;
+    if constexpr (S == 1) {
+        w[0] = (T)0;
+    } else if constexpr (S == 2) {
+        w[0] = (T)-1;
+        w[1] = one;
+    } else if constexpr (S == 3) {
+        w[0] = A::sub(t, half);
+        w[1] = A::mul((T)-2, t);
+        w[2] = A::add(t, half);
+    } else {
+        if (k.family == LI_LANCZOS) {
+            // d/dx [b sin(pi x) sin(c x) / x^2] = b (pi cos(pi x) sin(c x) + c sin(pi x) cos(c x) - 2 sin(pi x) sin(c x) / x) / x^2
+            constexpr int ctr = (S + 1) >> 1;
+#pragma unroll
+            for (int i = 1; i <= S; ++i) {
+                T x = (i < ctr) ? A::add(t, (T)(ctr - i)) : (i == ctr ? t : A::sub(t, (T)(i - ctr)));
+                T v;
+                if (A::abs_(x) >= k.c[0] || x == (T)0) {
+                    v = (T)0;
+                } else {
+                    const T px = A::mul(k.c[3], x), cx = A::mul(k.c[2], x);
+                    const T s1 = li_sin(px), c1 = li_cos(px), s2 = li_sin(cx), c2 = li_cos(cx);
+                    const T a1 = A::mul(A::mul(k.c[3], c1), s2);
+                    const T a2 = A::mul(A::mul(k.c[2], s1), c2);
+                    const T a3 = A::div(A::mul(A::mul(two, s1), s2), x);
+                    v = A::div(A::mul(k.c[1], A::sub(A::add(a1, a2), a3)), A::mul(x, x));
+                }
+                w[i - 1] = v;
+            }
+        } else if constexpr (S == 4) {
+            switch (k.family) {
+            case LI_CUBIC: {
+                T r = A::sub(one, t);
+                w[0] = A::mul(A::mul((T)-0.5, r), r);
+                w[1] = A::mul(A::sub(A::mul((T)1.5, t), two), t);
+                w[2] = A::mul(A::sub(two, A::mul((T)1.5, r)), r);
+                w[3] = A::mul(A::mul(half, t), t);
+                break;
+            }
+            case LI_CATMULLROM: {
+                w[0] = A::sub(A::mul(A::add(A::mul((T)-1.5, t), two), t), half);
+                w[1] = A::mul(A::sub(A::mul((T)4.5, t), (T)5), t);
+                w[2] = A::add(A::mul(A::add(A::mul((T)-4.5, t), (T)4), t), half);
+                w[3] = A::mul(A::sub(A::mul((T)1.5, t), one), t);
+                break;
+            }
+            case LI_CARDINALCUBIC: {
+                const T p = k.c[0], q = k.c[1];
+                T u = A::sub(one, t);
+                T tu = A::mul(t, u);
+                T umt = A::sub(u, t);
+                T q1tu = A::mul(A::add(one, q), tu);
+                w[0] = A::mul(p, A::mul(u, A::sub(u, A::add(t, t))));
+                w[1] = A::sub(A::sub(A::mul(A::sub(u, A::mul(q, t)), umt), q1tu), one);
+                w[2] = A::add(A::add(A::mul(A::sub(t, A::mul(q, u)), umt), q1tu), one);
+                w[3] = A::mul(p, A::mul(t, A::sub(A::add(u, u), t)));
+                break;
+            }
+            default: {
+                // Keys / Mitchell-Netravali: P'(x) = (3 p3 x + 2 p2) x, Q'(x) = (3 q3 x + 2 q2) x + q1
+                const T dp2 = A::mul(two, k.c[1]), dp3 = A::mul((T)3, k.c[2]);
+                const T dq1 = k.c[4], dq2 = A::mul(two, k.c[5]), dq3 = A::mul((T)3, k.c[6]);
+                auto P1 = [&](T x) { return A::mul(A::add(A::mul(dp3, x), dp2), x); };
+                auto Q1 = [&](T x) { return A::add(A::mul(A::add(A::mul(dq3, x), dq2), x), dq1); };
+                w[0] = Q1(A::add(t, one));
+                w[1] = P1(t);
+                w[2] = -P1(A::sub(one, t));
+                w[3] = -Q1(A::sub(two, t));
+                break;
+            }
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < S; ++s) w[s] = (T)0;  // unreachable: host validates (family, S)
+        }
+    }
+}
 
 // getweights(ker, t) for compile-time S (w fully in registers).
 template <typename T, int S>
@@ -200,6 +355,10 @@ __device__ __forceinline__ void getweights(const KerDev<T> &k, T t, T (&w)[S])
 {
     using A = Ar<T>;
     const T one = (T)1;
+    if (k.deriv) {   // the derivative kernels: d/dt of the expressions below
+        getweights_prime<T, S>(k, t, w);
+        return;
+    }
     if constexpr (S == 1) {
         w[0] = one;
     } else if constexpr (S == 2) {

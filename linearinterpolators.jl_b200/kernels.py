@@ -58,6 +58,7 @@ class Kernel:
     S = None
     nparams = 0
     defaults = ()
+    is_prime = False        # the derivative kernel `ker'` (`*Prime` types of src/LinearInterpolators.jl:23-41)
 
     def __init__(self, *args):
         T, B, params = _split_args(args)
@@ -98,11 +99,20 @@ class Kernel:
 
     def desc(self) -> _lib.KernelDesc:
         d = _lib.KernelDesc()
-        d.family, d.S, d.boundary = self.family, self.S, self.B.code
+        d.family, d.S, d.boundary = self.family | (_lib.PRIME if self.is_prime else 0), self.S, self.B.code
         d.dtype = _lib.F32 if self.T == np.dtype(np.float32) else _lib.F64
         for i in range(4):
             d.params[i] = self.params[i] if i < len(self.params) else 0.0
         return d
+
+    @property
+    def prime(self):
+        """``ker'``: the derivative kernel (same size, parameters, type and boundaries)."""
+        if self.is_prime:
+            raise _lib.ArgumentError("the second derivative of a kernel is not available")
+        k = object.__new__(_PRIME_OF[type(self)])
+        k.__dict__.update(self.__dict__)
+        return k
 
     def __repr__(self):
         p = ", ".join(f"{v:g}" for v in self.params)
@@ -158,5 +168,40 @@ class LanczosKernel(Kernel):
         self.params = ()
 
 
+# the derivative kernels: same constructors as their base kernels
+def _prime_class(base):
+    return type(base.__name__.replace("Spline", "SplinePrime").replace("Kernel", "KernelPrime"), (base,),
+                {"is_prime": True, "__doc__": f"Derivative of ``{base.__name__}`` (``{base.__name__}(...)'``)."})
+
+
+RectangularSplinePrime = _prime_class(RectangularSpline)
+LinearSplinePrime = _prime_class(LinearSpline)
+QuadraticSplinePrime = _prime_class(QuadraticSpline)
+CubicSplinePrime = _prime_class(CubicSpline)
+CatmullRomSplinePrime = _prime_class(CatmullRomSpline)
+CardinalCubicSplinePrime = _prime_class(CardinalCubicSpline)
+KeysSplinePrime = _prime_class(KeysSpline)
+MitchellNetravaliSplinePrime = _prime_class(MitchellNetravaliSpline)
+LanczosKernelPrime = _prime_class(LanczosKernel)
+_PRIME_OF = {c.__mro__[1]: c for c in (RectangularSplinePrime, LinearSplinePrime, QuadraticSplinePrime, CubicSplinePrime,
+                                       CatmullRomSplinePrime, CardinalCubicSplinePrime, KeysSplinePrime,
+                                       MitchellNetravaliSplinePrime, LanczosKernelPrime)}
+
+
 def boundaries(ker: Kernel):
     return ker.B
+
+
+def iscardinal(ker: Kernel) -> bool:
+    """``iscardinal(ker)``: ker(0) = 1 and ker(k) = 0 at the other integers (interpolating kernels)."""
+    if ker.is_prime:
+        return False
+    return ker.family in (RECTANGULAR, LINEAR, CATMULLROM, CARDINALCUBIC, KEYS, LANCZOS)
+
+
+def isnormalized(ker: Kernel) -> bool:
+    """``isnormalized(ker)``: the weights sum to one for every offset (the Lanczos kernel is not normalised)."""
+    if ker.is_prime:
+        return False
+    return ker.family != LANCZOS
+

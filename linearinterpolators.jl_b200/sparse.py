@@ -195,3 +195,97 @@ class SparseUnidimensionalInterpolator(AbstractSparseInterpolator):
         npre = int(np.prod(xd[:self.d - 1], dtype=np.int64))
         npost = int(np.prod(xd[self.d:], dtype=np.int64))
         return run_tab(self.table, P is Adjoint, npre, npost, alpha, x, beta, y, self.variant)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Normal equations of a 1-D fit (src/sparse.jl:277-490), on the device.
+RGL_EPS = 1e-9     # src/sparse.jl:358-359
+RGL_MU = 0.0
+
+
+def _normal_matrix(A: SparseInterpolator, w, device):
+    if not isinstance(A, SparseInterpolator):
+        raise TypeError("AtA / AtWA take a SparseInterpolator")
+    n = A.ncols
+    wd = None
+    if w is not None:
+        if ar.shape_of(w) != A.dims:
+            raise AssertionError("size(wgt) == output_size(A)")                         # :335
+        wd = w if ar.is_device(w) else ar.to_device(np.asfortranarray(np.asarray(w, dtype=A.eltype)))
+        if ar.np_dtype_of(wd) != A.eltype:
+            raise TypeError("weights must have the element type of the interpolator")
+        device = device or ar.is_device(w)
+    dst = ar.device_empty((n, n), A.eltype)
+    _lib.check(_lib.lib.li_table_atwa(A.table.handle, ar.data_ptr(wd) if wd is not None else None, ar.data_ptr(dst),
+                                      ar.current_stream(dst)))
+    return dst if device else ar.to_host(dst)
+
+
+def AtA(A: SparseInterpolator, device: bool = False):
+    """``AtA(A)`` = ``A'*A`` as a dense ``ncols x ncols`` matrix (src/sparse.jl:289-321), built on the device
+    (``li_table_atwa``); returned as a NumPy array unless ``device`` is set."""
+    return _normal_matrix(A, None, device)
+
+
+def AtWA(A: SparseInterpolator, w, device: bool = False):
+    """``AtWA(A, w)`` = ``A'*diag(w)*A`` (src/sparse.jl:277-287, 323-356); a device array of weights gives a device
+    result."""
+    return _normal_matrix(A, w, device)
+
+
+def regularize_(M, eps=RGL_EPS, mu=RGL_MU):
+    """``regularize!(A, eps, mu)`` (src/sparse.jl:445-490): ``A += rho*(eps*I + mu*D'*D)``, in place, host or device
+    square matrix."""
+    shp = ar.shape_of(M)
+    if len(shp) != 2 or shp[0] != shp[1]:
+        raise AssertionError("size(A,1) == size(A,2)")
+    if eps < 0 or mu < 0:
+        raise AssertionError("eps >= 0 && mu >= 0")
+    T = ar.np_dtype_of(M)
+    if ar.is_device(M):
+        status = _lib.lib.li_regularize(ar.li_dtype(T), ar.data_ptr(M), shp[0], float(eps), float(mu), ar.current_stream(M))
+        if status == _lib.ERR_ARG and b"we have a problem" in _lib.lib.li_last_error():
+            raise _lib.ErrorException("we have a problem!")
+        _lib.check(status)
+        return M
+    if not (isinstance(M, np.ndarray) and M.flags.f_contiguous):
+        raise TypeError("regularize_ works in place on a column-major NumPy array or a device array")
+    d = ar.to_device(M)
+    regularize_(d, eps, mu)
+    M[...] = ar.to_host(d)
+    return M
+
+
+def regularize(M, eps=RGL_EPS, mu=RGL_MU):
+    """``regularize(A, eps, mu)``: the regularized copy (src/sparse.jl:424-435)."""
+    if ar.is_device(M):
+        c = ar.device_empty(ar.shape_of(M), ar.np_dtype_of(M))
+        _lib.check(_lib.lib.li_memcpy_d2d(ar.data_ptr(c), ar.data_ptr(M), int(np.prod(ar.shape_of(M))) * ar.np_dtype_of(M).itemsize,
+                                          ar.current_stream(M)))
+        return regularize_(c, eps, mu)
+    return regularize_(np.array(M, order="F", copy=True), eps, mu)
+
+
+def fit(A: SparseInterpolator, y, w=None, epsilon=RGL_EPS, mu=RGL_MU):
+    """``fit(A, y [, w]; epsilon, mu)`` (src/sparse.jl:361-422): the minimiser of ``sum(w .* (A*x - y).^2)`` plus the
+    regularization of ``regularize``.  The right-hand side ``A'*(w .* y)`` and the matrix ``A'*W*A`` are built on the
+    device; the (small, dense) Cholesky solve runs on the host in Float64.  (The reference's own method calls
+    ``cholfact!``, removed in Julia 1.0, and its unweighted method reads an undefined ``w``: this is the intended
+    behaviour, fixed forward.)"""
+    yh = np.asfortranarray(np.asarray(ar.to_host(y) if ar.is_device(y) else y, dtype=A.eltype))
+    if yh.shape != A.dims:
+        raise AssertionError("size(y) == output_size(A)")
+    if w is not None:
+        wh = np.asfortranarray(np.asarray(ar.to_host(w) if ar.is_device(w) else w, dtype=A.eltype))
+        if wh.shape != yh.shape:
+            raise AssertionError("size(w) == size(y)")
+        rhs = np.asarray(A.adj * np.asfortranarray(wh * yh))
+        lhs = AtWA(A, wh)
+    else:
+        rhs = np.asarray(A.adj * yh)
+        lhs = AtA(A)
+    lhs = np.asfortranarray(lhs)
+    regularize_(lhs, epsilon, mu)
+    import scipy.linalg as sl
+    c = sl.cho_factor(np.asarray(lhs, dtype=np.float64))
+    return sl.cho_solve(c, np.asarray(rhs, dtype=np.float64)).astype(A.eltype)

@@ -128,6 +128,26 @@ double lio_sin_f64(double x)
     }
 }
 
+/* cos(x): the same reduction, the kernels of the next quadrant (msun s_cos.c). */
+double lio_cos_f64(double x)
+{
+    double ax = fabs(x);
+    if (ax < 0.78539816339744830962) return kcos(x, 0.0);
+    if (!(ax < INFINITY)) return x - x;
+    double y0, y1;
+    int n = rem_pio2_medium(x, &y0, &y1) & 3;
+    switch (n) {
+    case 0:
+        return kcos(y0, y1);
+    case 1:
+        return -ksin(y0, y1, 1);
+    case 2:
+        return -kcos(y0, y1);
+    default:
+        return ksin(y0, y1, 1);
+    }
+}
+
 /* Float32: everything is evaluated in Float64 and rounded once (k_sindf/k_cosdf). */
 #define FS1 bits_f64(0xBFC5555554CBAC77ull) /* -0x15555554cbac77.0p-55 */
 #define FS2 bits_f64(0x3F811110896EFBB2ull) /*  0x111110896efbb2.0p-59 */
@@ -181,6 +201,27 @@ float lio_sin_f32(float x)
     }
 }
 
+float lio_cos_f32(float x)
+{
+    float ax = fabsf(x);
+    if (ax < 0.78539818525314331f) return kcosdf((double)x);
+    if (!(ax < INFINITY)) return x - x;
+    double xd = (double)x;
+    double fn = rint(xd * INVPIO2);
+    int n = (int)fn & 3;
+    double y = (xd - fn * FPIO2_1) - fn * FPIO2_1T;
+    switch (n) {
+    case 0:
+        return kcosdf(y);
+    case 1:
+        return -ksindf(y);
+    case 2:
+        return -kcosdf(y);
+    default:
+        return ksindf(y);
+    }
+}
+
 /* Error-scale helpers for the tests (tests/util.py): the on-the-fly and affine loops can be run with every weight
  * replaced by its magnitude (mode 1: "the same operator applied with |w| to |src|", the per-element error bound of
  * SURVEY.md Appendix F) or by 1 where it is non-zero (mode 2: the number of products summed into an element). */
@@ -208,6 +249,7 @@ int lio_max_threads(void)
 #define RINT rintf
 #define FLOOR floorf
 #define SIN lio_sin_f32
+#define COS lio_cos_f32
 #include "li_oracle_impl.inc"
 #undef T
 #undef SFX
@@ -217,6 +259,7 @@ int lio_max_threads(void)
 #undef RINT
 #undef FLOOR
 #undef SIN
+#undef COS
 
 #define T double
 #define SFX f64
@@ -226,4 +269,5 @@ int lio_max_threads(void)
 #define RINT rint
 #define FLOOR floor
 #define SIN lio_sin_f64
+#define COS lio_cos_f64
 #include "li_oracle_impl.inc"

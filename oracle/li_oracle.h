@@ -56,18 +56,22 @@ typedef struct {
     int32_t family;
     int32_t S;
     int32_t boundary;
-    int32_t reserved;
+    int32_t prime; /* != 0: the derivative kernel (`*Prime`, src/LinearInterpolators.jl:23-41): getweights yields d/dt */
     double p[2];
 } lio_kernel;
 
 /* sin() restated from the msun algorithm Julia's Base.sin follows, without FMA. */
 double lio_sin_f64(double x);
 float lio_sin_f32(float x);
+double lio_cos_f64(double x);
+float lio_cos_f32(float x);
 
 #define LIO_DECLARE(T, SFX)                                                                       \
     void lio_limits_##SFX(const lio_kernel *k, int64_t len, T *inf, T *sup);                      \
     int lio_getweights_##SFX(const lio_kernel *k, T t, T *w);                                     \
     int lio_getcoefs_##SFX(const lio_kernel *k, int64_t len, T x, int64_t *j, T *w);              \
+    int lio_AtWA_##SFX(int S, int64_t nrows, const int64_t *J, const T *C, int64_t ncols, const T *w, T *dst); \
+    int lio_regularize_##SFX(T *A, int64_t n, T eps, T mu);                                       \
     int lio_maketable_##SFX(const lio_kernel *k, const T *x, int64_t nrows, int64_t ncols,        \
                             int64_t *J, T *W);                                                    \
     void lio_fractional_index_##SFX(const T *pos, int64_t n, T first, T step, T last,             \

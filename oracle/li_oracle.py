@@ -30,7 +30,7 @@ class InexactError(ArithmeticError):
 
 class KernelDesc(C.Structure):
     _fields_ = [("family", C.c_int32), ("S", C.c_int32), ("boundary", C.c_int32),
-                ("reserved", C.c_int32), ("p", C.c_double * 2)]
+                ("prime", C.c_int32), ("p", C.c_double * 2)]
 
 
 def build(force: bool = False) -> str:
@@ -58,9 +58,10 @@ def lib():
     return _lib
 
 
-def kernel(family: int, S: int, boundary: int = FLAT, params=()) -> KernelDesc:
+def kernel(family: int, S: int, boundary: int = FLAT, params=(), prime: bool = False) -> KernelDesc:
+    """`prime`: the derivative kernel (`*Prime` of src/LinearInterpolators.jl:23-41)."""
     k = KernelDesc()
-    k.family, k.S, k.boundary, k.reserved = family, S, boundary, 0
+    k.family, k.S, k.boundary, k.prime = family, S, boundary, int(bool(prime))
     p = list(params) + [0.0, 0.0]
     k.p[0], k.p[1] = float(p[0]), float(p[1])
     return k
@@ -285,3 +286,25 @@ class weight_mode:
 
 def max_threads() -> int:
     return int(lib().lio_max_threads())
+
+
+def AtWA(J, W, ncols: int, w=None):
+    """AtA! / AtWA! -- src/sparse.jl:299-356: dense A'*diag(w)*A (w None: A'*A) of the table (J, W)."""
+    dtype = W.dtype
+    S, nrows = W.shape
+    dst = np.empty((ncols, ncols), dtype=dtype, order="F")
+    wv = None if w is None else np.ascontiguousarray(np.asarray(w, dtype=dtype).reshape(-1, order="F"))
+    st = getattr(lib(), "lio_AtWA_" + _sfx(dtype))(C.c_int(S), C.c_int64(nrows), _p(np.asfortranarray(J)), _p(np.asfortranarray(W)),
+                                                   C.c_int64(ncols), _p(wv) if wv is not None else None, _p(dst))
+    if st != 0:
+        raise RuntimeError("corrupted interpolator table")
+    return dst
+
+
+def regularize(A, eps, mu):
+    """regularize! -- src/sparse.jl:451-490, on a copy."""
+    A = np.array(A, order="F", copy=True)
+    st = getattr(lib(), "lio_regularize_" + _sfx(A.dtype))(_p(A), C.c_int64(A.shape[0]), _ct(A.dtype)(eps), _ct(A.dtype)(mu))
+    if st != 0:
+        raise RuntimeError("we have a problem!")
+    return A
