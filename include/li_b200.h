@@ -198,6 +198,12 @@ LI_API int li_otf1d_apply(int adjoint, const li_kernel_desc *ker, const void *x_
  * src/separable.jl:56-162.  Direct: src[m1,m2,nbatch] -> dst[n1,n2,nbatch].
  * Coefficients are generated on the device per call (no table survives the call).
  * Synchronous. */
+/* N-d separable with on-the-fly coefficients, ndim = 1..3 (the generalisation the reference plans, src/separable.jl:14):
+ * one kernel and one position vector per dimension; tables are generated on the device for this call, then the fused
+ * 2-D / 3-D kernels run.  Direct: src[m_1..m_ndim, nbatch] -> dst[n_1..n_ndim, nbatch].  Synchronous. */
+LI_API int li_sep_otf_apply(int adjoint, int ndim, const li_kernel_desc *const *kers, const void *const *x_dev,
+                            const int64_t *n, const int64_t *m, int64_t nbatch, double alpha, const void *src_dev,
+                            double beta, void *dst_dev, void *stream);
 LI_API int li_sep2d_otf_apply(int adjoint, const li_kernel_desc *ker1, const void *x1_dev, int64_t n1,
                        const li_kernel_desc *ker2, const void *x2_dev, int64_t n2, int64_t m1,
                        int64_t m2, int64_t nbatch, double alpha, const void *src_dev, double beta,

@@ -29,6 +29,41 @@ function apply!(α::Real, ::Type{P}, ker1::Kernel{T,S1}, x1::AbstractVector{T}, 
 end
 
 """
+    apply!(α, P, ker1, x1, ker2, x2, ker3, x3, src, β, dst)
+
+three dimensions with on-the-fly coefficients (`li_sep_otf_apply`): the extension of src/separable.jl:56-162 the
+reference plans (src/separable.jl:14).  Tables are generated on the device for this call, then the fused 3-D kernels run.
+"""
+function apply!(α::Real, ::Type{P}, ker1::Kernel{T}, x1::AbstractVector{T}, ker2::Kernel{T}, x2::AbstractVector{T},
+                ker3::Kernel{T}, x3::AbstractVector{T}, src::AbstractArray{T,3}, β::Real,
+                dst::AbstractArray{T,3}) where {P<:Union{Direct,Adjoint},T<:Floats}
+    n = Int64[length(x1), length(x2), length(x3)]
+    if P === Direct
+        @assert size(dst) == Tuple(n)
+        m = Int64[size(src)...]
+    else
+        @assert size(src) == Tuple(n)
+        m = Int64[size(dst)...]
+    end
+    (src isa DeviceArray) == (dst isa DeviceArray) ||
+        error("source and destination must both be host arrays or both be device arrays")
+    ds = (DeviceArray(collect(x1)), DeviceArray(collect(x2)), DeviceArray(collect(x3)))
+    dsrc = src isa DeviceArray ? src : DeviceArray(convert(Array{T}, src))
+    ddst = dst isa DeviceArray ? dst : DeviceArray(convert(Array{T}, dst))
+    descs = [kernel_desc(ker1), kernel_desc(ker2), kernel_desc(ker3)]
+    GC.@preserve descs ds dsrc ddst begin
+        kp = Ptr{Cvoid}[pointer(descs, k) for k in 1:3]
+        xp = Ptr{Cvoid}[d.ptr for d in ds]
+        check(ccall((:li_sep_otf_apply, LIB), Cint,
+                    (Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, Int64, Cdouble, Ptr{Cvoid}, Cdouble,
+                     Ptr{Cvoid}, Ptr{Cvoid}),
+                    P === Adjoint, 3, kp, xp, n, m, 1, α, dsrc.ptr, β, ddst.ptr, C_NULL))
+    end
+    dst isa DeviceArray || copyto!(dst, Array(ddst))
+    return dst
+end
+
+"""
     sep_apply!(α, P, (A1, A2[, A3]), x, β, y)
 
 applies `A1*A2[*A3]` (or its adjoint), `Ak` interpolating dimension `k`, in one call of `li_sep_apply[_host]`
@@ -153,6 +188,16 @@ function sep_apply_tables!(α::Real, ::Type{P}, slots::Vector, x::HostOrDevice{T
     dims = Int64[size(x)...]
     GC.@preserve slots x y begin
         if x isa DeviceArray
+            # two tables on dimensions 1-2 or three tables on dimensions 1-3 normally run as ONE fused kernel that needs
+            # no workspace: try that first (LI_ERR_ARG = 1 "workspace too small" when the fused kernels decline)
+            st = ccall((:li_sep_apply, LIB), Cint,
+                       (Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Int64, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid},
+                        Csize_t, Cint, Ptr{Cvoid}),
+                       P === Adjoint, N, handles, dims, 1, α, x, β, y, C_NULL, 0, 0, C_NULL)
+            if st == 0
+                check(ccall((:li_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+                return y
+            end
             need = Ref{Csize_t}(0)
             check(ccall((:li_sep_workspace_bytes, LIB), Cint, (Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Int64, Ptr{Csize_t}),
                         P === Adjoint, N, handles, dims, 1, need))

@@ -18,7 +18,7 @@ from .kernels import (Boundaries, CardinalCubicSpline, CardinalCubicSplinePrime,
 from .mapping import (Adjoint, AdjointMapping, Composition, Direct, Gram, LinearMapping, Mapping, Operations,
                       Table, apply, apply_, apply_b, vcreate, vdot)
 from .nonseparable import AffineTransform2D, TwoDimensionalTransformInterpolator, affine_apply, intercept, rotate
-from .separable import sep2d_otf_apply, sep_apply_batch, sep_apply_tables
+from .separable import sep2d_otf_apply, sep_apply_batch, sep_apply_tables, sep_otf_apply
 from .sparse import (AtA, AtWA, Range, SparseInterpolator, SparseUnidimensionalInterpolator, fit, fractional_index,
                      regularize, regularize_)
 from .tabulated import TabulatedInterpolator, coefficients, columns, ncols, nrows, width

@@ -138,6 +138,8 @@ _PROTOS = {
     "li_allreduce_sum": (_int, [_vp, _int, _vp, _i64, _vp]),
     "li_adjoint_accumulate_allreduce": (_int, [_vp, _int, _i64, _i64, _i64, C.POINTER(_vp), C.POINTER(_vp), _dbl, _dbl, _vp,
                                                _int, _vp]),
+    "li_sep_otf_apply": (_int, [_int, _int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), _i64, _dbl, _vp, _dbl,
+                         _vp, _vp]),
     "li_table_atwa": (_int, [_vp, _vp, _vp, _vp]),
     "li_regularize": (_int, [_int, _vp, _i64, _dbl, _dbl, _vp]),
     "li_vdot": (_int, [_int, _vp, _vp, _i64, C.POINTER(_dbl), _vp]),

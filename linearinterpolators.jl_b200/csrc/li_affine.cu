@@ -23,6 +23,46 @@ extern template int affine_adjoint_gather<float>(const li_kernel_desc *, const l
                                                  int64_t, int64_t, double, const void *, double, void *, int *, cudaStream_t, bool *);
 extern template int affine_adjoint_gather<double>(const li_kernel_desc *, const li_kernel_desc *, const double[6], int64_t, int64_t, int64_t,
                                                   int64_t, int64_t, double, const void *, double, void *, int *, cudaStream_t, bool *);
+
+// positions of an axis-aligned transform: x[i] = c * convert(T, i + 1) + off, product and sum rounded separately as in
+// the reference (R.xx*pos1 + off1, src/nonseparable.jl:163-168)
+template <typename T>
+__global__ void axis_positions_kernel(T c, T off, int64_t n, T *__restrict__ x)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if constexpr (sizeof(T) == 4)
+        x[i] = __fadd_rn(__fmul_rn(c, (T)(i + 1)), off);
+    else
+        x[i] = __dadd_rn(__dmul_rn(c, (T)(i + 1)), off);
+}
+
+// Aligned axes (R.xy == 0 and R.yx == 0: scaling + translation): the reference's FIXME "if axes are aligned, use
+// separable interpolation" (src/nonseparable.jl:14).  The positions R.xx*i1 + (R.xy*i2 + R.x) do not depend on i2 (0*i2
+// is exactly 0), R.yx*i1 + (R.yy*i2 + R.y) not on i1, so the coefficients are those of two per-dimension tables (bit
+// for bit) and the operator is the separable one: HBM-bound fused kernels instead of the L1-bound tiled gather.
+template <typename T>
+static int affine_aligned(int adjoint, const li_kernel_desc *ker1, const li_kernel_desc *ker2, const double R[6], int64_t n1, int64_t n2,
+                          int64_t m1, int64_t m2, int64_t nbatch, double alpha, const void *src, double beta, void *dst,
+                          cudaStream_t st)
+{
+    void *x1 = nullptr;
+    int rc = staging(8, (size_t)(n1 + n2) * sizeof(T), &x1, (void *)st);
+    if (rc != LI_OK) return rc;
+    T *px1 = (T *)x1, *px2 = px1 + n1;
+    const T xy = (T)R[1], yx = (T)R[3];
+    // off1 = R.xy*pos2 + R.x with R.xy == 0, off2 = R.yy*pos2 + R.y is the dim-2 position itself
+    const T off1 = (T)(xy * (T)1) + (T)R[2];
+    axis_positions_kernel<T><<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>((T)R[0], off1, n1, px1);
+    axis_positions_kernel<T><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>((T)R[4], (T)R[5], n2, px2);
+    count_launch(2);
+    LI_CUDA(cudaGetLastError());
+    (void)yx;
+    const li_kernel_desc *kers[2] = {ker1, ker2};
+    const void *xs[2] = {px1, px2};
+    const int64_t n[2] = {n1, n2}, m[2] = {m1, m2};
+    return li_sep_otf_apply(adjoint, 2, kers, xs, n, m, nbatch, alpha, src, beta, dst, (void *)st);
+}
 }  // namespace li
 
 extern "C" int li_affine2d_apply(int adjoint, const li_kernel_desc *ker1, const li_kernel_desc *ker2,
@@ -47,6 +87,12 @@ extern "C" int li_affine2d_apply(int adjoint, const li_kernel_desc *ker1, const 
     if (alpha == 0.0) return li::vscale_impl(dtype, dst_dev, nout, beta, st);  // :169-172
     LI_REQUIRE(src_dev, LI_ERR_ARG, "null source");
     if (n1 == 0 || n2 == 0) return li::vscale_impl(dtype, dst_dev, nout, beta, st);
+    if (R[1] == 0.0 && R[3] == 0.0 && variant != LI_VARIANT_ATOMIC && !li::opt(li::OPT_AFFINE_PLAIN) && !(li::opt(li::OPT_EXP) & 4)) {
+        // (x2 = R.yx*pos1 + off2 with R.yx == 0: 0*pos1 + off2 == off2 unless off2 is -0, which getcoefs treats alike)
+        if (li::opt(li::OPT_TRACE)) fprintf(stderr, "[li_b200] affine: aligned axes -> separable on-the-fly operator\n");
+        return dtype == LI_F32 ? li::affine_aligned<float>(adjoint, ker1, ker2, R, n1, n2, m1, m2, nbatch, alpha, src_dev, beta, dst_dev, st)
+                               : li::affine_aligned<double>(adjoint, ker1, ker2, R, n1, n2, m1, m2, nbatch, alpha, src_dev, beta, dst_dev, st);
+    }
     static thread_local std::map<int, int *> d_errs;   // per device
     int *&d_err = d_errs[li::current_device()];
     if (!d_err) LI_CUDA(cudaMalloc(&d_err, sizeof(int)));

@@ -70,9 +70,10 @@ int vscale_impl(int dtype, void *y, int64_t n, double beta, cudaStream_t st)
 // streams must not share buffers.
 struct StageSet {
     // 0: src, 1: dst, 2: workspace, 3: partial accumulators, 4: frame pointers, 5: partial models of frame groups,
-    // 6: rank-private accumulator of the all-reduce, 7: spare
-    void *ptr[8] = {};
-    size_t bytes[8] = {};
+    // 6: rank-private accumulator of the all-reduce, 7: vector-verb partial sums, 8: positions of an axis-aligned affine
+    // operator, 9: scalars of regularize!
+    void *ptr[10] = {};
+    size_t bytes[10] = {};
 };
 static thread_local std::map<std::pair<int, void *>, StageSet> g_stage;   // key: (device, stream)
 

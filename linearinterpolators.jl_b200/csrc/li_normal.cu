@@ -108,7 +108,7 @@ int li_regularize(int dtype, void *A_dev, int64_t n, double eps, double mu, void
     if (!(eps > 0.0) && !(mu > 0.0)) return LI_OK;
     cudaStream_t st = li::as_stream(stream);
     void *rho = nullptr;
-    int rc = li::staging(7, 16, &rho, stream);
+    int rc = li::staging(9, 16, &rho, stream);
     if (rc != LI_OK) return rc;
     double rho_host = 0.0;
     if (dtype == LI_F32) {

@@ -427,38 +427,57 @@ int li_otf1d_apply(int adjoint, const li_kernel_desc *ker, const void *x_dev, in
     return rc;
 }
 
-int li_sep2d_otf_apply(int adjoint, const li_kernel_desc *ker1, const void *x1_dev, int64_t n1,
-                       const li_kernel_desc *ker2, const void *x2_dev, int64_t n2, int64_t m1, int64_t m2,
-                       int64_t nbatch, double alpha, const void *src_dev, double beta, void *dst_dev, void *stream)
+int li_sep_otf_apply(int adjoint, int ndim, const li_kernel_desc *const *kers, const void *const *x_dev, const int64_t *n,
+                     const int64_t *m, int64_t nbatch, double alpha, const void *src_dev, double beta, void *dst_dev,
+                     void *stream)
 {
-    LI_REQUIRE(ker1 && ker2 && dst_dev, LI_ERR_ARG, "null argument");
-    LI_REQUIRE(ker1->dtype == ker2->dtype, LI_ERR_ARG, "kernels must share one floating-point type");
+    LI_REQUIRE(ndim >= 1 && ndim <= 3, LI_ERR_UNSUPPORTED, "on-the-fly separable operators support 1 to 3 dimensions");
+    LI_REQUIRE(kers && x_dev && n && m && dst_dev, LI_ERR_ARG, "null argument");
+    for (int k = 0; k < ndim; ++k) {
+        LI_REQUIRE(kers[k], LI_ERR_ARG, "null kernel");
+        LI_REQUIRE(kers[k]->dtype == kers[0]->dtype, LI_ERR_ARG, "kernels must share one floating-point type");
+    }
     cudaStream_t st = li::as_stream(stream);
-    li_table *t[2] = {nullptr, nullptr};
-    int rc = li::table_create_impl(ker1, x1_dev, n1, m1, st, &t[0]);
-    if (rc == LI_OK) rc = li::table_create_impl(ker2, x2_dev, n2, m2, st, &t[1]);
+    li_table *t[3] = {nullptr, nullptr, nullptr};
+    int rc = LI_OK;
+    for (int k = 0; k < ndim && rc == LI_OK; ++k) rc = li::table_create_impl(kers[k], x_dev[k], n[k], m[k], st, &t[k]);
     void *ws = nullptr;
     size_t wsb = 0;
-    if (rc == LI_OK) rc = li_sep_workspace_bytes(adjoint, 2, t, nullptr, nbatch, &wsb);
-    if (rc == LI_OK && wsb) {
-        cudaError_t e = cudaMalloc(&ws, wsb);
-        if (e != cudaSuccess) {
-            li::set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
-            rc = LI_ERR_NOMEM;
+    // (the fused kernels need no workspace: try without, and only allocate the scratch of the per-dimension passes
+    // when they decline)
+    if (rc == LI_OK) {
+        rc = li::sep_apply_impl(adjoint, ndim, t, nullptr, nbatch, alpha, src_dev, beta, dst_dev, nullptr, 0, LI_VARIANT_AUTO, st);
+        if (rc == LI_ERR_ARG && strstr(li_last_error(), "workspace too small")) {
+            rc = li_sep_workspace_bytes(adjoint, ndim, t, nullptr, nbatch, &wsb);
+            if (rc == LI_OK && wsb) {
+                cudaError_t e = cudaMalloc(&ws, wsb);
+                if (e != cudaSuccess) {
+                    li::set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
+                    rc = LI_ERR_NOMEM;
+                }
+            }
+            if (rc == LI_OK)
+                rc = li::sep_apply_impl(adjoint, ndim, t, nullptr, nbatch, alpha, src_dev, beta, dst_dev, ws, wsb, LI_VARIANT_AUTO, st);
         }
     }
-    if (rc == LI_OK)
-        rc = li::sep_apply_impl(adjoint, 2, t, nullptr, nbatch, alpha, src_dev, beta, dst_dev, ws, wsb,
-                                LI_VARIANT_AUTO, st);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(ws);
-    li_table_destroy(t[0]);
-    li_table_destroy(t[1]);
+    for (int k = 0; k < ndim; ++k) li_table_destroy(t[k]);
     if (rc == LI_OK && e != cudaSuccess) {
         li::set_error("on-the-fly separable apply failed: %s", cudaGetErrorString(e));
         rc = LI_ERR_CUDA;
     }
     return rc;
+}
+
+int li_sep2d_otf_apply(int adjoint, const li_kernel_desc *ker1, const void *x1_dev, int64_t n1,
+                       const li_kernel_desc *ker2, const void *x2_dev, int64_t n2, int64_t m1, int64_t m2,
+                       int64_t nbatch, double alpha, const void *src_dev, double beta, void *dst_dev, void *stream)
+{
+    const li_kernel_desc *kers[2] = {ker1, ker2};
+    const void *xs[2] = {x1_dev, x2_dev};
+    const int64_t n[2] = {n1, n2}, m[2] = {m1, m2};
+    return li_sep_otf_apply(adjoint, 2, kers, xs, n, m, nbatch, alpha, src_dev, beta, dst_dev, stream);
 }
 
 }  // extern "C"

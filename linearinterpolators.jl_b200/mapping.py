@@ -343,6 +343,7 @@ def apply_b(*args):
     * ``apply!(alpha, P, ker, x, src, beta, dst)`` / ``apply!(dst, [P,] ker, x, src)`` -- src/unidimensional.jl:58-245
     * ``apply!(alpha, P, ker1, x1, ker2, x2, src, beta, dst)`` / ``apply!(dst, [P,] ker1, x1, [ker2,] x2, src)`` -- src/separable.jl
     * ``apply!(alpha, P, ker1, [ker2,] R, src, beta, dst)`` / ``apply!(dst, [P,] ker1, [ker2,] R, src)`` -- src/nonseparable.jl
+    * ``apply!(alpha, P, ker1, x1, ker2, x2, ker3, x3, src, beta, dst)`` -- three dimensions on the fly (``sep_otf_apply``)
     """
     from .nonseparable import AffineTransform2D, affine_apply
     from .separable import sep2d_otf_apply
@@ -393,6 +394,9 @@ def apply_b(*args):
         if len(mid) == 4:
             ker, x1, x2, src = mid
             return sep2d_otf_apply(alpha, P, ker, x1, ker, x2, src, beta, y)
+        if len(mid) == 7 and all(isinstance(m, Kernel) for m in mid[0:6:2]):   # three dimensions (beyond the reference)
+            from .separable import sep_otf_apply
+            return sep_otf_apply(alpha, P, mid[0:6:2], mid[1:6:2], mid[6], beta, y)
     raise TypeError("apply!: no method matching these arguments")
 
 

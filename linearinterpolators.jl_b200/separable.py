@@ -151,3 +151,51 @@ def sep2d_otf_apply(alpha, P, ker1, x1, ker2, x2, src, beta, dst):
     if not dev:
         dst[...] = ar.to_host(ddst)
     return dst
+
+
+def sep_otf_apply(alpha, P, kers, xs, src, beta, dst):
+    """N-d (1 to 3 dimensions) separable interpolation with on-the-fly coefficients: one kernel and one vector of
+    positions per dimension -- the generalisation of src/separable.jl:56-162 the reference plans (src/separable.jl:14
+    "use a table for the innermost dimensions").  Tables are generated on the device for this call
+    (``li_sep_otf_apply``), then the fused 2-D / 3-D kernels run."""
+    nd = len(kers)
+    if nd != len(xs) or not 1 <= nd <= 3:
+        raise TypeError("one kernel and one position vector per dimension (1 to 3 dimensions)")
+    T = kers[0].T
+    if any(k.T != T for k in kers):
+        raise TypeError("kernels must have the same floating-point type")
+    adjoint = P is Adjoint
+    src = ar.to_colmajor(src, T)
+    ns = tuple(int(np.prod(ar.shape_of(x))) for x in xs)
+    ss, ds = ar.shape_of(src), ar.shape_of(dst)
+    if len(ss) != nd or len(ds) != nd:
+        raise TypeError(f"source and destination must be {nd}-dimensional")
+    if (ss if adjoint else ds) != ns:
+        raise AssertionError("size(src) == map(length, x)" if adjoint else "size(dst) == map(length, x)")
+    ms = ds if adjoint else ss
+    check_dst(dst, ds, T)
+    check_same_kind(src, dst)
+    dev = ar.is_device(dst)
+
+    def dev_vec(x):
+        if ar.is_device(x):
+            if ar.np_dtype_of(x) != T:
+                raise TypeError("device positions must have the kernel's floating-point type")
+            return x
+        return ar.to_device(np.ascontiguousarray(np.asarray(x).ravel(), dtype=T), device=dst.device if ar.is_torch(dst) else None)
+
+    dxs = [dev_vec(x) for x in xs]
+    if dev:
+        dsrc, ddst = src, dst
+    else:
+        dsrc = ar.to_device(src)
+        ddst = ar.empty_like_kind(dsrc, ds, T) if float(beta) == 0.0 else ar.to_device(dst)
+    descs = [k.desc() for k in kers]
+    kp = (C.c_void_p * nd)(*[C.cast(C.pointer(d), C.c_void_p) for d in descs])
+    xp = (C.c_void_p * nd)(*[ar.data_ptr(x) for x in dxs])
+    na, ma = (C.c_int64 * nd)(*ns), (C.c_int64 * nd)(*ms)
+    _lib.check(_lib.lib.li_sep_otf_apply(int(adjoint), nd, kp, xp, na, ma, 1, float(alpha), ar.data_ptr(dsrc), float(beta),
+                                         ar.data_ptr(ddst), ar.current_stream(ddst)))
+    if not dev:
+        dst[...] = ar.to_host(ddst)
+    return dst

@@ -466,6 +466,70 @@ def test_affine(li, T):
 
 
 @pytest.mark.parametrize("T", DTYPES)
+def test_affine_aligned_axes_take_the_separable_kernels(li, T):
+    """src/nonseparable.jl:14 "if axes are aligned, use separable interpolation": a scaling + translation (R.xy = R.yx
+    = 0) runs through the separable on-the-fly operator (per-dimension tables, fused kernels); same results as the
+    oracle's affine loops and as the library's own affine kernels (exp bit 4 switches the shortcut off)."""
+    rng = np.random.default_rng(77)
+    rows, cols = (96, 70), (64, 52)
+    R = li.AffineTransform2D(0.61, 0.0, 1.7, 0.0, 0.77, -0.4, T=T)     # (xx, xy, x, yx, yy, y): corners hang over the edges
+    Rc = np.array(R.coefs())
+    for e1, e2 in ((KERNELS[4], KERNELS[8]), (KERNELS[1], KERNELS[3]), (KERNELS[9], KERNELS[9])):
+        k1, k2 = product_kernel(li, e1, O.FLAT, T), product_kernel(li, e2, O.SAFEFLAT, T)
+        o1, o2 = oracle_kernel(e1, O.FLAT), oracle_kernel(e2, O.SAFEFLAT)
+        A = li.TwoDimensionalTransformInterpolator(rows, cols, k1, k2, R)
+        x = np.asfortranarray(rng.standard_normal(cols).astype(T))
+        y = np.asfortranarray(rng.standard_normal(rows).astype(T))
+        dx, dy = li.to_device(x), li.to_device(y)
+        got, gota = li.to_host(A * dx), li.to_host(A.adj * dy)
+        assert_close(got, O.affine2d(False, o1, o2, Rc, rows, cols, x, T), T)
+        assert_close(gota, O.affine2d(True, o1, o2, Rc, rows, cols, y, T), T)
+        li.set_option("exp", 4)
+        try:
+            plain, plaina = li.to_host(A * dx), li.to_host(A.adj * dy)
+        finally:
+            li.set_option("exp", 0)
+        assert_close(plain, O.affine2d(False, o1, o2, Rc, rows, cols, x, T), T)
+        assert_close(plaina, O.affine2d(True, o1, o2, Rc, rows, cols, y, T), T)
+        d0 = np.asfortranarray(rng.standard_normal(rows).astype(T))
+        ref = O.affine2d(False, o1, o2, Rc, rows, cols, x, T, -0.5, 2, d0.copy(order="F"))
+        dd = li.to_device(d0)
+        li.apply_b(-0.5, li.Direct, A, dx, False, 2, dd)
+        assert_close(li.to_host(dd), ref, T)
+    with pytest.raises(li.InexactError):   # a NaN coordinate raises like the affine loops (trunc(Int, NaN))
+        li.TwoDimensionalTransformInterpolator(rows, cols, k1, k2, li.AffineTransform2D(1.0, 0.0, np.nan, 0.0, 1.0, 0.0, T=T)) * dx
+
+
+@pytest.mark.parametrize("T", DTYPES)
+def test_sep3d_on_the_fly(li, T):
+    """Three dimensions with on-the-fly coefficients (li_sep_otf_apply): same numbers as three table-backed operators."""
+    rng = np.random.default_rng(78)
+    m, n = (24, 20, 12), (40, 31, 19)
+    ents = (KERNELS[4], KERNELS[3], KERNELS[1])
+    xs = [np.linspace(0.5, m[d] + 0.75, n[d]).astype(T) for d in range(3)]
+    kers = [product_kernel(li, ents[d], O.FLAT, T) for d in range(3)]
+    JW = [O.maketable(oracle_kernel(ents[d], O.FLAT), xs[d], m[d], T) for d in range(3)]
+    src = np.asfortranarray(rng.standard_normal(m).astype(T))
+    y = np.asfortranarray(rng.standard_normal(n).astype(T))
+    for dev in (False, True):
+        s, yy = (li.to_device(src), li.to_device(y)) if dev else (src, y)
+        out = li.device_empty(n, T) if dev else np.empty(n, dtype=T, order="F")
+        li.apply_b(1, li.Direct, kers[0], xs[0], kers[1], xs[1], kers[2], xs[2], s, 0, out)
+        ref = src
+        for d in (2, 1, 0):
+            ref = O.tab_direct(JW[d][0], JW[d][1], m[d], d + 1, ref)
+        assert_close(li.to_host(out) if dev else out, ref, T)
+        back = li.device_empty(m, T) if dev else np.empty(m, dtype=T, order="F")
+        li.apply_b(1, li.Adjoint, kers[0], xs[0], kers[1], xs[1], kers[2], xs[2], yy, 0, back)
+        refa = y
+        for d in (0, 1, 2):
+            refa = O.tab_adjoint(JW[d][0], JW[d][1], m[d], d + 1, refa)
+        assert_close(li.to_host(back) if dev else back, refa, T)
+    with pytest.raises(AssertionError):
+        li.apply_b(1, li.Direct, kers[0], xs[0], kers[1], xs[1], kers[2], xs[2][:-1], src, 0, np.empty(n, dtype=T, order="F"))
+
+
+@pytest.mark.parametrize("T", DTYPES)
 @pytest.mark.parametrize("theta,scale", [(0.2, 1.0), (0.785, 1.0), (1.45, 1.0), (-2.6, 0.35), (0.4, 3.1)])
 def test_affine_tiled_batch(li, T, theta, scale):
     """The tiled forward (TMA-staged source boxes, several images in flight) against the oracle image by image and,
