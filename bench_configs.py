@@ -138,7 +138,14 @@ def cfg5(li, torch, nframes):
         acc.zero_()
         li.sep_apply_batch(True, tabs, 1, views, 1, [acc] * nframes)
     t = timeit(run_batch, 3, warm=1)
-    report(f"#5 same, li_sep_apply_batch (one library call for all {nframes} frames)",
+    report(f"#5 same, li_sep_apply_batch (one library call for all {nframes} frames; handles marshalled per call)",
+           nframes * m * m, nframes * m * m * 4 + m * m * 4, *t)
+    batch = li.FrameBatch([tuple(t) for t in tabs], views)   # handles and pointers marshalled once, as a fit would
+
+    def run_multi():
+        li.adjoint_accumulate(batch, acc)
+    t = timeit(run_multi, 3, warm=1)
+    report(f"#5 same, li_adjoint_accumulate_allreduce on a FrameBatch (multi-frame kernel, one launch)",
            nframes * m * m, nframes * m * m * 4 + m * m * 4, *t)
 
 
