@@ -484,29 +484,30 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
     auto run_generic = [&](auto clean, auto hasbeta) {
         const T *pw = sW2;
         const int *pa = sNv;
-        int nskip = va - v0;    // leading rows of the window that belong to the previous chunk (or lie before the array)
         int vcur = v0;
+        // (dp follows vcur: the leading rows v0 .. va-1 of the window belong to the previous chunk, or lie before the array,
+        // and are never stored -- a predicate, not a branch)
+        T *dq = dp - (int64_t)(va - v0) * dstep;
         T oldq[S2];             // beta != 0: old values of the next S2 rows to be stored, read S2 rows ahead
         if constexpr (decltype(hasbeta)::value) {
 #pragma unroll
             for (int i = 0; i < S2; ++i) oldq[i] = oldv[(S2 - 1 + i) % S2];
         }
         auto advance = [&]() {   // dst row vcur (slot 0) is complete
-            if (nskip > 0) {
-                --nskip;
+            const bool owned = vcur >= va;
+            if constexpr (!decltype(hasbeta)::value) {   // dst is never read
+                if (have && owned) *dq = acc[0];
             } else {
-                if constexpr (!decltype(hasbeta)::value) {   // dst is never read
-                    if (have) *dp = acc[0];
-                } else {
+                if (owned) {
                     const T o = fmaT(betav, oldq[0], acc[0]);
-                    if (have) *dp = o;
+                    if (have) *dq = o;
 #pragma unroll
                     for (int i = 0; i + 1 < S2; ++i) oldq[i] = oldq[i + 1];
                     oldq[S2 - 1] = (T)0;
-                    if (ld_old && vcur + S2 < vb) oldq[S2 - 1] = dp[(int64_t)S2 * dstep];
+                    if (ld_old && vcur + S2 < vb) oldq[S2 - 1] = dq[(int64_t)S2 * dstep];
                 }
-                dp += dstep;
             }
+            dq += dstep;
 #pragma unroll
             for (int s = 0; s + 1 < S2; ++s) acc[s] = acc[s + 1];
             acc[S2 - 1] = (T)0;
@@ -519,8 +520,12 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
             for (int r = 0; r < K; ++r) {
                 if (r < nr) {   // block-uniform: only the last stage is partial
                     const int ad = pa[r];
+                    int n = ad & 0xffff;
+                    if (n) {               // (mostly one row)
+                        advance();
 #pragma unroll 1
-                    for (int n = ad & 0xffff; n > 0; --n) advance();
+                        for (--n; n > 0; --n) advance();
+                    }
                     const T val = gather(prow, clean);
                     prow += rowstep;
                     T w2[S2];

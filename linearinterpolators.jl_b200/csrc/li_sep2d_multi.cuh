@@ -898,11 +898,14 @@ static int multi_build_plan(int64_t n, const li_table *const *tabs, int row_lo, 
     plan->ntiles = (int)tl.size();
     plan->CRMAX = CR;
     plan->NS = NS;
-    // frame groups: enough CTAs to fill the machine, then four times as many as resident slots when every group keeps
+    // frame groups: enough CTAs to fill the machine, then several times as many as resident slots when every group keeps
     // at least 8 frames -- tiles differ in cost (edge strips and edge chunks run slower loops), and with more CTAs than
     // slots the hardware scheduler evens that out (measured on config #5: 10.0 -> 7.9 us per frame)
     const int64_t g_fill = std::max<int64_t>(1, (slots + plan->ntiles / 2) / plan->ntiles);
-    plan->G = (int)std::max<int64_t>(1, std::max(std::min<int64_t>(g_fill, n / 4), std::min<int64_t>(4 * g_fill, n / 8)));
+    // (measured, frames -> best G with g_fill = 1: 64 -> 3, 128 -> 6, 512 -> 12; the groups of a tile are combined at the end,
+    // so short batches want fewer of them)
+    const int64_t g_over = n >= 256 ? 12 : (n >= 96 ? 6 : 3);
+    plan->G = (int)std::max<int64_t>(1, std::max(std::min<int64_t>(g_fill, n / 4), std::min<int64_t>(g_over * g_fill, n / 8)));
     if (opt(OPT_ADJ_DEBUG) >= 11 && opt(OPT_ADJ_DEBUG) <= 26) plan->G = opt(OPT_ADJ_DEBUG) - 10;   // (experiments)
 
     // ---- pass 2: per (frame, tile) geometry (+ most src rows feeding a tile)
