@@ -265,7 +265,8 @@ LI_API int li_allreduce_sum(li_comm *comm, int dtype, void *buf_dev, int64_t cou
  * tabs[2k], tabs[2k+1] are the dim-1 / dim-2 tables of local frame k (ncols = m1 / m2), src_dev[k] its data
  * [nrows_1, nrows_2].  comm == NULL: this GPU only.  A rank may own zero frames.  The model is produced in `nbands`
  * bands of rows; the all-reduce of a band overlaps the computation of the next one (nbands <= 16; 1 = a single
- * all-reduce at the end: the measured optimum on a node of B200s for config #5 -- every band is a launch over all the
+ * all-reduce at the end -- with one process per GPU the library's own two-shot all-reduce over NVLink peer memory (CUDA
+ * IPC exchange buffers, rank-ordered sums: the same bits on every rank), else ncclAllReduce: the measured optimum on a node of B200s for config #5 -- every band is a launch over all the
  * local frames, and on 2 GPUs 2 / 4 bands took 3.2 / 2.9 ms against 2.1 ms with the 0.09 ms all-reduce exposed).  Deterministic for a given number of ranks, bands and frame order.  Asynchronous on
  * `stream` (the communicator's own stream is joined back into it before the call returns). */
 LI_API int li_adjoint_accumulate_allreduce(li_comm *comm, int dtype, int64_t m1, int64_t m2, int64_t nframes,

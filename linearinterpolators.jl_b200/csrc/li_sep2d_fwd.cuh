@@ -382,7 +382,13 @@ static int launch_fwd(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     // chunks of output rows: FWD_WAVES_ whole waves of the CTAs resident per SM (the kernel's launch bound), chunk
     // length a multiple of 8 and at most FWD_MAXCR
     constexpr int PER_SM = (sizeof(T) == 4 && S1 <= 4 && S2 <= 4) ? 4 : (sizeof(T) == 4 ? 3 : 2);
-    const int64_t target = (int64_t)sep2d_num_sms() * PER_SM * FWD_WAVES_;
+    // (measured, scratch/waves_probe.py: the narrow Float32 kernels -- four CTAs per SM -- on integer resampling rates run
+    // fastest in four waves of shorter chunks, 65 -> 59 us on config #2: less idle time at the end of the grid; wide
+    // kernels and fractional rates in two)
+    int waves = FWD_WAVES_;
+    if (!D3 && PER_SM == 4 && a.m2 > 0 && a.n2 % a.m2 == 0) waves = 4;
+    if (const int o = (opt(OPT_EXP) >> 8) & 15) waves = o;   // (development: li_set_option("exp", waves << 8))
+    const int64_t target = (int64_t)sep2d_num_sms() * PER_SM * waves;
     int chunks = (int)std::max<int64_t>(1, target / (a.tiles1 * nbatch));   // (rounded down: whole waves)
     int CR = (a.n2 + chunks - 1) / chunks;
     CR = std::min(FWD_MAXCR, std::max(8, (CR + 7) & ~7));

@@ -59,6 +59,42 @@ def _worker(rank, world, port, out_dir):
                 want += O.tab_adjoint(J2, W2, m, 2, O.tab_adjoint(J1, W1, m, 1, yk)).astype(np.float64)
             err = np.max(np.abs(got - want)) / np.max(np.abs(want))
             ok = ok and err <= 1e-5
+    # the same exchange step through the C ABI: the multi-frame kernel on the local frames + the library's own
+    # all-reduce (peer memory over NVLink when the ranks can map each other's buffers, else NCCL)
+    lo, hi = li.shard_range(nframes, rank, world)
+    loc = [_frame_ops(li, T, m, k) for k in range(lo, hi)]
+    tabs = [(A1.table, A2.table) for A1, A2, _, _ in loc]
+    views = [li.to_device(np.asfortranarray(frames[k])) for k in range(lo, hi)]
+    results = {}
+    fails = []
+    model0 = np.asfortranarray(rng.standard_normal((m, m)).astype(T))         # same on every rank (same seed)
+    for name, exp in (("peer", 0), ("nccl", 8)):
+        li.set_option("exp", exp)                 # (read when the communicator first needs its exchange buffers)
+        comm = li.Comm.from_torch_distributed()
+        for beta in (0.0, 0.5):
+            model = li.to_device(model0.copy(order="F"))
+            li.adjoint_accumulate(tabs, views, model, alpha=1, beta=beta, comm=comm)
+            results[(name, beta)] = li.to_host(model)
+            if rank == 0:
+                ref = beta * model0.astype(np.float64) + want
+                err = np.max(np.abs(results[(name, beta)] - ref)) / np.max(np.abs(ref))
+                if not err <= 1e-5:
+                    fails.append(f"{name} beta={beta}: rel err {err:.3e}")
+        big = torch.full((1 << 19,), float(rank + 1), device="cuda", dtype=torch.float32)      # 2 MB: the peer path
+        small = torch.full((1000,), float(rank + 1), device="cuda", dtype=torch.float64)      # NCCL
+        comm.allreduce_sum(big)
+        comm.allreduce_sum(small)
+        tot = world * (world + 1) / 2
+        if not bool((big == tot).all().item()):
+            fails.append(f"{name}: all-reduce of the large buffer")
+        if not bool((small == tot).all().item()):
+            fails.append(f"{name}: all-reduce of the small buffer")
+        torch.cuda.synchronize()
+        comm.destroy()
+    li.set_option("exp", 0)
+    for beta in (0.0, 0.5):      # two ranks: a + b in either order, so both all-reduces give the same bits
+        if not np.array_equal(results[("peer", beta)], results[("nccl", beta)]):
+            fails.append(f"peer and nccl results differ, beta={beta}: {np.max(np.abs(results[('peer', beta)] - results[('nccl', beta)])):.3e}")
     # batch of images sharded over ranks (forward, no communication)
     nb = 6
     lo, hi = li.shard_range(nb, rank, world)
@@ -70,7 +106,7 @@ def _worker(rank, world, port, out_dir):
     ref = O.tab_direct(A1.J, A1.W, m, 1, O.tab_direct(A2.J, A2.W, m, 2, np.asfortranarray(imgs[:, :, lo:hi])))
     ok = ok and np.max(np.abs(li.to_host(out) - ref)) <= 2e-6 * np.max(np.abs(ref))
     with open(os.path.join(out_dir, f"r{rank}.txt"), "w") as f:
-        f.write("ok" if ok else "bad")
+        f.write("ok" if ok and not fails else "bad: " + "; ".join(fails))
     dist.barrier()
     dist.destroy_process_group()
 
