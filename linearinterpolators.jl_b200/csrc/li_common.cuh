@@ -32,7 +32,8 @@ enum Option {
     OPT_NO_MULTI,          // multi-frame accumulate kernel off: one launch per frame
     OPT_EXP,               // development: bit mask of A/B switches (2: 3-D applies without the fused 3-D kernels,
                            // 4: affine operators with aligned axes without the separable shortcut,
-                           // 8: all-reduces through NCCL only (no peer-memory all-reduce))
+                           // 8: all-reduces through NCCL only (no peer-memory all-reduce);
+                           // bits 8..11: waves of CTAs of the fused forward kernel, 0 = the built-in choice)
     OPT_COUNT
 };
 extern std::atomic<int> g_options[OPT_COUNT];

@@ -4,6 +4,7 @@
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 P=gpurun_out/r2z
+python -c "import __graft_entry__ as g; g.smoke()" > ${P}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 ${P}_smoke.log
 timeout 900 python bench.py > ${P}_bench.json 2> ${P}_bench.err; echo "bench rc=$?"
 timeout 600 python bench_configs.py --batch3 8 --frames5 128 > ${P}_configs.log 2>&1; echo "configs rc=$?"
 timeout 600 python scratch/spectrum_probe.py > ${P}_spectrum.log 2>&1; echo "spectrum rc=$?"
