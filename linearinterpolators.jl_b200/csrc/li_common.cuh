@@ -69,6 +69,7 @@ inline int current_device()
     cudaGetDevice(&dev);
     return dev;
 }
+constexpr int LI_HEAVY_COLUMN = 512;
 inline size_t dtype_size(int dtype) { return dtype == LI_F32 ? 4 : 8; }
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -94,6 +95,10 @@ struct li_table {
     // generic transposed (CSC) table: entries sorted by (column, row, tap)
     mutable int32_t *colptr = nullptr;  // [ncols+1]
     mutable int32_t *tent = nullptr;    // [nrows*S] entry id e = row*S + tap
+    // columns with more than LI_HEAVY_COLUMN entries (Flat clamping piles every row hanging over an edge onto the
+    // first / last column): summed by a whole CTA each in the gather adjoint (li_tab_apply.cu), not by one thread
+    mutable int32_t *heavy = nullptr;   // [nheavy] column indices
+    mutable int nheavy = 0;
     // monotone windowed tables: bptr[j] = first row with base >= j-(S-1), j in [0, ncols+S-1] (see li_table.cu)
     mutable int32_t *rowstart = nullptr;
     // adjoint of the fused kernels: windows folded into [0, ncols) (clamped taps merged into the first/last tap)

@@ -105,6 +105,7 @@ tab_adjoint_gather_d1_kernel(const int32_t *__restrict__ colptr, const int32_t *
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ncols) return;
     const int e0 = colptr[j], e1 = colptr[j + 1];
+    if (e1 - e0 > LI_HEAVY_COLUMN) return;   // (a heavy column: tab_adjoint_heavy_d1_kernel)
     for (int64_t q = blockIdx.y; q < npost; q += gridDim.y) {
         const T *sp = src + q * nrows;
         T *d = dst + q * ncols + j;
@@ -115,6 +116,43 @@ tab_adjoint_gather_d1_kernel(const int32_t *__restrict__ colptr, const int32_t *
             acc = fma_(W[ent], x, acc);
         }
         *d = acc;
+    }
+}
+
+// Heavy columns of the same operator (more than LI_HEAVY_COLUMN entries: with Flat clamping the first / last column
+// collect every row hanging over that edge): one CTA per (heavy column, slice).  Thread t sums the t-th contiguous
+// segment of the column's entries in ascending order, the 256 partial sums are combined by a fixed tree: deterministic
+// (the order of the sums is fixed by the table alone), O(entries / 256 + 8) steps instead of O(entries) on one thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+tab_adjoint_heavy_d1_kernel(const int32_t *__restrict__ heavy, const int32_t *__restrict__ colptr, const int32_t *__restrict__ tent,
+                            const T *__restrict__ W, int S, int nrows, int ncols, int64_t npost, T alpha, T beta,
+                            const T *__restrict__ src, T *__restrict__ dst)
+{
+    __shared__ T part[256];
+    const int j = heavy[blockIdx.x];
+    const int e0 = colptr[j], e1 = colptr[j + 1];
+    const int seg = (e1 - e0 + 255) / 256;
+    const int a = min(e0 + (int)threadIdx.x * seg, e1), b = min(a + seg, e1);
+    for (int64_t q = blockIdx.y; q < npost; q += gridDim.y) {
+        const T *sp = src + q * nrows;
+        T acc = (T)0;
+        for (int e = a; e < b; ++e) {
+            const int ent = tent[e];
+            const T x = alpha == (T)1 ? sp[ent / S] : alpha * sp[ent / S];
+            acc = fma_(W[ent], x, acc);
+        }
+        part[threadIdx.x] = acc;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) part[threadIdx.x] = part[threadIdx.x] + part[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            T *d = dst + q * ncols + j;
+            *d = beta == (T)0 ? part[0] : fma_(beta, *d, part[0]);
+        }
+        __syncthreads();
     }
 }
 
@@ -519,6 +557,12 @@ static int adjoint_T(const li_table *t, int64_t npre, int64_t npost, double alph
         dim3 grid((ncols + 255) / 256, (unsigned)std::min<int64_t>(npost, 65535));
         tab_adjoint_gather_d1_kernel<T><<<grid, 256, 0, st>>>(t->colptr, t->tent, (const T *)t->W, t->S, nrows,
                                                              ncols, npost, a, b, (const T *)src, (T *)dst);
+        if (t->nheavy > 0) {
+            count_launch();
+            dim3 hgrid((unsigned)t->nheavy, (unsigned)std::min<int64_t>(npost, 65535));
+            tab_adjoint_heavy_d1_kernel<T><<<hgrid, 256, 0, st>>>(t->heavy + 1, t->colptr, t->tent, (const T *)t->W, t->S, nrows, ncols,
+                                                                 npost, a, b, (const T *)src, (T *)dst);
+        }
     } else {
         const int threads = npre >= 256 ? 256 : (npre >= 128 ? 128 : (npre >= 64 ? 64 : 32));
         dim3 grid((unsigned)((npre + threads - 1) / threads), std::min(ncols, 65535),

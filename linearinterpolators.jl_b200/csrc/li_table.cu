@@ -324,6 +324,12 @@ int table_create_impl(const li_kernel_desc *ker, const void *pos_dev, int64_t nr
     return LI_OK;
 }
 
+__global__ void heavy_columns_kernel(const int32_t *__restrict__ colptr, int ncols, int threshold, int32_t *count, int32_t *list)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < ncols && colptr[j + 1] - colptr[j] > threshold) list[atomicAdd(count, 1)] = j;   // (list order is irrelevant)
+}
+
 int table_ensure_csc(const li_table *t, cudaStream_t st)
 {
     std::lock_guard<std::mutex> lock(t->mu);
@@ -370,11 +376,22 @@ int table_ensure_csc(const li_table *t, cudaStream_t st)
     colptr_kernel<<<(unsigned)((t->ncols + 1 + 255) / 256), 256, 0, st>>>(keys_out, n, (int)t->ncols, colptr);
     count_launch();
     LI_TRY(cudaGetLastError());
+    // heavy columns (more than LI_HEAVY_COLUMN entries): listed once, for the segmented sums of the gather adjoint
+    int32_t *heavy = nullptr;
+    int nheavy = 0;
+    const int64_t cap = n / LI_HEAVY_COLUMN + 1;
+    LI_TRY(cudaMalloc(&heavy, (cap + 1) * sizeof(int32_t)));
+    LI_TRY(cudaMemsetAsync(heavy, 0, sizeof(int32_t), st));
+    heavy_columns_kernel<<<(unsigned)((t->ncols + 255) / 256), 256, 0, st>>>(colptr, (int)t->ncols, LI_HEAVY_COLUMN, heavy, heavy + 1);
+    count_launch();
+    LI_TRY(cudaMemcpyAsync(&nheavy, heavy, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     LI_TRY(cudaStreamSynchronize(st));
 #undef LI_TRY
     cleanup();
     t->tent = vals_out;
     t->colptr = colptr;
+    t->heavy = heavy;        // ([0] is the counter, the list follows)
+    t->nheavy = nheavy;
     return rc;
 }
 
@@ -857,6 +874,7 @@ int li_table_destroy(li_table *t)
     cudaFree(t->base);
     cudaFree(t->colptr);
     cudaFree(t->tent);
+    cudaFree(t->heavy);
     cudaFree(t->rowstart);
     cudaFree(t->Wfold);
     cudaFree(t->bfold);

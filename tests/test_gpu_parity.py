@@ -308,6 +308,21 @@ def test_gather_adjoint_is_deterministic(li):
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     J, W = O.maketable(O.kernel(O.LANCZOS, 6), xs.astype(T), 64, T)
     assert_close(outs[0], O.tab_adjoint(J, W, 64, 1, li.to_host(y)), T, factor=50)
+    # the heavy columns (here the first and the last one: thousands of entries each) are summed by a CTA each, in
+    # segments combined by a fixed tree; several slices, both element types, alpha / beta
+    for TT in DTYPES:
+        A2 = li.TabulatedInterpolator(TT, 1, li.LanczosKernel(TT, 6), xs, 64)
+        J2, W2 = O.maketable(O.kernel(O.LANCZOS, 6), xs.astype(TT), 64, TT)
+        assert max(np.bincount(J2.ravel())) > 2000
+        y2 = np.asfortranarray(rng.standard_normal((5000, 3)).astype(TT))
+        d0 = np.asfortranarray(rng.standard_normal((64, 3)).astype(TT))
+        got = []
+        for _ in range(2):
+            dd = li.to_device(d0.copy(order="F"))
+            li.apply_b(0.5, li.Adjoint, A2, li.to_device(y2), False, 2, dd)
+            got.append(li.to_host(dd))
+        assert np.array_equal(got[0], got[1])
+        assert_close(got[0], O.tab_adjoint(J2, W2, 64, 1, y2, 0.5, 2, d0.copy(order="F")), TT)
 
 
 def test_imported_arbitrary_table(li):
