@@ -168,9 +168,13 @@ LI_API int li_tab_apply(int adjoint, const li_table *t, int64_t npre, int64_t np
  * k), the LazyAlgebra composition of test/benchmarks.jl:27-29,44-49.  A NULL entry
  * in `tabs` leaves that dimension untouched (its length is dims_in[k]).
  * Direct : src [ncols_1..ncols_n, nbatch] -> dst [nrows_1..nrows_n, nbatch];
- * Adjoint: the reverse.  ndim = 2 uses a fused kernel (one pass over HBM) when
- * both tables are windowed; otherwise per-dimension passes through `workspace`.
- * `dims_other[k]` is only read for NULL tables. */
+ * Adjoint: the reverse.  Two tables on dimensions 1-2 (any pair of kernel sizes of
+ * {2,3,4,6,8}^2; plus untouched / batch dimensions) and three tables on dimensions
+ * 1-3 run as ONE fused kernel (one pass over HBM, no workspace: `workspace_dev` may
+ * be NULL -- the call fails with LI_ERR_ARG "workspace too small" only if the fused
+ * kernels decline the problem) when the tables are windowed and monotone; otherwise
+ * per-dimension passes through `workspace`.  `dims_other[k]` is only read for NULL
+ * tables. */
 LI_API int li_sep_workspace_bytes(int adjoint, int ndim, const li_table *const *tabs,
                            const int64_t *dims_other, int64_t nbatch, size_t *bytes);
 LI_API int li_sep_apply(int adjoint, int ndim, const li_table *const *tabs, const int64_t *dims_other,

@@ -9,12 +9,15 @@
 // Both tables must be "windowed" and monotone: row i reads columns clamp(base[i] + s, 0, ncols-1), s = 0..S-1, with
 // non-decreasing bases -- what getcoefs (src/boundaries.jl:87-156) produces for sorted positions.
 //
-//   forward : sep2d_fwd_kernel (this file): a streaming register pipeline fed by a ring of TMA bulk copies.
+//   forward : sep2d_fwd_kernel (li_sep2d_fwd.cuh): a streaming register pipeline fed by a ring of TMA bulk copies.
 //   adjoint : sep2d_adj_stream_kernel (li_sep2d_adjs.cuh): the same data flow run backwards; it is tried first and
 //             declines what it cannot stage.  The tile-owned kernels of this file (sep2d_adj_regular_kernel,
 //             sep2d_adj_kernel: dim-2 accumulation from global memory into a shared-memory intermediate, then a
 //             dim-1 gather) are the fallback for unaligned sources and for down-sampling along dim 1.
 //   No kernel uses atomics; every dst element is written once by its owner, in a fixed order (deterministic).
+//   This file: the tile-owned adjoint kernels, the dispatch over the kernel-size pairs (the eight original pairs + the
+//   identity pairs here, the other pairs of {2,3,4,6,8}^2 in li_sep2d_more_*.cu) and the banded host-buffer pipeline.
+//   Three dimensions: li_sep3d.cuh (the same two streaming kernels with a third factor applied while staging).
 #include <algorithm>
 #include <map>
 
