@@ -142,8 +142,11 @@ int table_tile_rows(const li_table *t, int TD2, cudaStream_t st, const int32_t *
 // `nchunks` chunks of columns of about equal cost for the streaming adjoint: a chunk holding a column that is not
 // fed by exactly reg_R rows (or touches a folded window) runs the slower generic loop and is made shorter by `penalty`
 // (fraction of a chunk).  *starts (device) has nchunks+1 boundaries.
+// `weights` (optional, one per chunk; `weights_key` < 2^14 identifies them in the plan cache): relative shares of the
+// chunks instead of equal ones.
 int table_chunk_plan(const li_table *t, int nchunks, double penalty, cudaStream_t st, const int32_t **starts, int *crmax,
-                     int *nrmax, const li_table::ChunkPlan **plan = nullptr);
+                     int *nrmax, const li_table::ChunkPlan **plan = nullptr, const std::vector<double> *weights = nullptr,
+                     int weights_key = 0);
 int table_base_host(const li_table *t, cudaStream_t st, const std::vector<int32_t> **base);
 int table_identity(int dtype, int64_t n, cudaStream_t st, const li_table **out);   // cached S = 1 identity operator
 // builds a table from device positions into preallocated device arrays (used by the OTF operators)

@@ -59,6 +59,9 @@ struct AdsK {   // src rows per stage: a multiple of 2*S2 so that the static sch
     static constexpr int value = D3 ? ((S2 == 6 || S2 == 3) ? 6 : (S2 == 8 ? 8 : 4))
                                     : ((S2 == 6 || S2 == 3) ? 12 : (S2 == 8 ? 16 : ADS_K_));
 };
+#ifndef ADS_TAPER_
+#define ADS_TAPER_ 8   // chunk taper of single-wave launches, in eighths of the measured imbalance (0 = equal chunks)
+#endif
 #ifndef ADS3_NSR_
 #define ADS3_NSR_ 2
 #endif
@@ -101,6 +104,10 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
     const int chunk = bid % a.tiles2 + a.chunk0;
     const int64_t batch = bid / a.tiles2;
     const int c0 = strip * NT, c1 = min(c0 + NT, a.m1);      // owned dst columns
+#ifdef ADS_PROBE
+    unsigned long long probe_t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(probe_t0));
+#endif
     const int va = a.cstart[chunk], vb = a.cstart[chunk + 1];   // owned dst rows (chunks of about equal cost, <= CR rows)
     if (va >= vb) return;                                    // (empty chunk: block-uniform, before any barrier)
     const int v0 = va - (S2 - 1);                            // first dst row the chunk's src rows reach
@@ -568,6 +575,14 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
         run(std::true_type{});
     else
         run(std::false_type{});
+#ifdef ADS_PROBE   // timing probe (development builds): start / end of every CTA on the global timer
+    if (a.rowlist && tid == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        unsigned long long *p = (unsigned long long *)a.rowlist + 2 * (size_t)blockIdx.x;
+        p[0] = probe_t0, p[1] = t1;
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -662,7 +677,37 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     // chunks that must run the generic loop (array edges, irregular rates) are charged 30 % of a chunk, i.e. made
     // shorter: all CTAs of the single wave then finish together
     const li_table::ChunkPlan *plan = nullptr;
-    rc = table_chunk_plan(t2, nchunks, 0.3, st, &a.cstart, &CR, &nrmax, &plan);
+    // One image in one wave: the CTAs of a grid are handed to the SMs in index order, one per SM and round, and an SM
+    // favours its older CTAs (measured with the ADS_PROBE build on config #2: with equal chunks the first CTA of an SM
+    // finishes at 48 us, the second at 50.5, the third at 54, the fourth at 60.5, and the SM runs under-occupied from
+    // 48 us on).  The chunks are therefore tapered: longer for the CTAs scheduled first, shorter for the last ones.
+    std::vector<double> taper;
+    int taper_key = 0;
+    {
+        const int strength = ((opt(OPT_EXP) >> 12) & 15) ? ((opt(OPT_EXP) >> 12) & 15) - 1 : ADS_TAPER_;   // (x/8; exp bits 12..15: value + 1)
+        const int nsm = sep2d_num_sms();
+        if (!D3 && nbatch == 1 && occ >= 2 && strength > 0 && (int64_t)nchunks * a.tiles1 <= (int64_t)nsm * occ && a.tiles1 < 128) {
+            static const double shape[4] = {0.18, 0.10, 0.0, -0.14};   // (second iteration of the probe)
+            taper.resize((size_t)nchunks);
+            for (int c = 0; c < nchunks; ++c) {
+                double w = 0.0;
+                for (int sx = 0; sx < a.tiles1; ++sx) {
+                    const int slot = std::min((c * a.tiles1 + sx) / nsm, occ - 1);
+                    // position of the slot within the rounds, mapped onto the four measured ones
+                    const double pos = occ > 1 ? 3.0 * slot / (occ - 1) : 0.0;
+                    const int lo = (int)pos;
+                    const double f = pos - lo;
+                    w += 1.0 + strength / 8.0 * (shape[lo] * (1.0 - f) + shape[std::min(lo + 1, 3)] * f);
+                }
+                taper[(size_t)c] = w / a.tiles1;
+            }
+            // (the chunks at the array edges run the slower generic loop: no bonus on top of their penalty)
+            taper[0] = std::min(taper[0], 1.0);
+            taper[(size_t)nchunks - 1] = std::min(taper[(size_t)nchunks - 1], 1.0);
+            taper_key = a.tiles1 | (strength << 7) | (occ << 11);   // (< 2^14)
+        }
+    }
+    rc = table_chunk_plan(t2, nchunks, 0.3, st, &a.cstart, &CR, &nrmax, &plan, taper.empty() ? nullptr : &taper, taper_key);
     if (rc != LI_OK) return rc;
     if (CR > 4096) return LI_OK;
 #ifdef ADS_OLD_GENERIC
@@ -694,6 +739,13 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
 #ifdef ADS_ABLATE
     if (opt(OPT_ADJ_DEBUG) == 4) a.vec_ok = 77;
 #endif
+#ifdef ADS_PROBE
+    unsigned long long *probe = nullptr;
+    if (opt(OPT_ADJ_DEBUG) == 5) {
+        LI_CUDA(cudaMalloc((void **)&probe, (size_t)blocks * 2 * sizeof(unsigned long long)));
+        a.rowlist = (const int32_t *)probe;   // (unused by this kernel: carries the probe buffer)
+    }
+#endif
 #define LI_ADS(NUU, RR) \
     if (NU == NUU && R == RR) rc = launch_stream<T, S1, S2, NUU, RR, D3>(a, CR, NRMAX, smem, blocks, st);
     LI_ADS(NU_S, 0) LI_ADS(NU_L, 0)
@@ -701,6 +753,33 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
         LI_ADS(NU_S, 1) LI_ADS(NU_S, 2) LI_ADS(NU_L, 1) LI_ADS(NU_L, 2)
     }
 #undef LI_ADS
+#ifdef ADS_PROBE
+    if (probe) {
+        std::vector<unsigned long long> h((size_t)blocks * 2);
+        cudaMemcpy(h.data(), probe, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        cudaFree(probe);
+        a.rowlist = nullptr;
+        unsigned long long t0 = ~0ull, t1 = 0;
+        for (int64_t b = 0; b < blocks; ++b) t0 = std::min(t0, h[2 * b]), t1 = std::max(t1, h[2 * b + 1]);
+        fprintf(stderr, "[li_b200] adj probe: %lld CTAs, kernel span %.1f us\n", (long long)blocks, (t1 - t0) * 1e-3);
+        for (int c = 0; c < a.tiles2; ++c) {
+            double s0 = 0, s1 = 0, mx = 0;
+            for (int sx = 0; sx < a.tiles1; ++sx) {
+                const int64_t b = (int64_t)c * a.tiles1 + sx;
+                s0 += (h[2 * b] - t0) * 1e-3, s1 += (h[2 * b + 1] - t0) * 1e-3, mx = std::max(mx, (h[2 * b + 1] - t0) * 1e-3);
+            }
+            fprintf(stderr, "[li_b200] adj probe chunk %3d: start %.1f end %.1f (latest %.1f) us\n", c, s0 / a.tiles1, s1 / a.tiles1, mx);
+        }
+        for (int sx = 0; sx < a.tiles1; ++sx) {
+            double s1 = 0, mx = 0;
+            for (int c = 0; c < a.tiles2; ++c) {
+                const int64_t b = (int64_t)c * a.tiles1 + sx;
+                s1 += (h[2 * b + 1] - h[2 * b]) * 1e-3, mx = std::max(mx, (h[2 * b + 1] - t0) * 1e-3);
+            }
+            fprintf(stderr, "[li_b200] adj probe strip %3d: mean duration %.1f us, latest end %.1f us\n", sx, s1 / a.tiles2, mx);
+        }
+    }
+#endif
     if (rc == LI_OK) *done = true;
     return rc;
 }

@@ -695,12 +695,13 @@ int table_base_host(const li_table *t, cudaStream_t st, const std::vector<int32_
 }
 
 int table_chunk_plan(const li_table *t, int nchunks, double penalty, cudaStream_t st, const int32_t **starts, int *crmax,
-                     int *nrmax, const li_table::ChunkPlan **plan_out)
+                     int *nrmax, const li_table::ChunkPlan **plan_out, const std::vector<double> *weights, int weights_key)
 {
     int rc = table_ensure_fold(t, st);
     if (rc != LI_OK) return rc;
     std::lock_guard<std::mutex> lock(t->mu);
-    auto it = t->chunk_plans.find(nchunks);
+    const int key = weights ? (nchunks | (weights_key << 12)) : nchunks;   // (nchunks < 4096: CR >= 8 rows)
+    auto it = t->chunk_plans.find(key);
     if (it == t->chunk_plans.end()) {
         const int m = (int)t->ncols, S = t->S;
         std::vector<int32_t> bpf(m + S), irrp(m + 1, 0);
@@ -719,10 +720,13 @@ int table_chunk_plan(const li_table *t, int nchunks, double penalty, cudaStream_
             cost[v + 1] = total;
             prev = odd;
         }
+        // share of chunk k: equal, or proportional to weights[k] (CTAs that the hardware favours get longer chunks)
+        std::vector<double> cum(nchunks + 1, 0.0);
+        for (int k = 0; k < nchunks; ++k) cum[k + 1] = cum[k] + (weights ? (*weights)[k] : 1.0);
         std::vector<int32_t> b(nchunks + 1, 0);
         int v = 0;
         for (int k = 1; k < nchunks; ++k) {
-            const double want = total * k / nchunks;
+            const double want = total * cum[k] / cum[nchunks];
             while (v < m && cost[v] < want) ++v;
             b[k] = std::max(v, b[k - 1]);
         }
@@ -744,7 +748,7 @@ int table_chunk_plan(const li_table *t, int nchunks, double penalty, cudaStream_
             set_error("chunk plan upload failed: %s", cudaGetErrorString(e));
             return LI_ERR_CUDA;
         }
-        it = t->chunk_plans.emplace(nchunks, plan).first;
+        it = t->chunk_plans.emplace(key, plan).first;
     }
     *starts = it->second.starts;
     *crmax = it->second.crmax;
