@@ -120,13 +120,48 @@ class SparseInterpolator(AbstractSparseInterpolator):
         x = ar.to_colmajor(x, self.eltype)
         return ar.empty_like_kind(x, self.dims if P is Direct else (self.ncols,), self.eltype)  # :187-199
 
+    def _promoted_table(self):
+        """The same table with its Float32 weights converted (exactly) to Float64: the arithmetic type
+        ``float(promote_type(Ta, Tx))`` of src/sparse.jl:214,250 when Float64 data meet a Float32 operator."""
+        if getattr(self, "_table64", None) is None:
+            self._table64 = Table.from_arrays(self.table.J, self.table.W.astype(np.float64), self.ncols)
+        return self._table64
+
+    def _apply_mixed(self, alpha, P, x, beta, y):
+        """Host arrays whose element types differ from the operator's (src/sparse.jl:201-275 accepts ``Tx<:Real``,
+        ``Ty<:AbstractFloat``): the sums run in ``T = float(promote_type(Ta, Tx))`` on the device, the result is
+        combined with ``beta*y`` and converted to ``Ty`` on the host."""
+        Tx, Ty, Ta = np.dtype(np.asarray(x).dtype), np.dtype(y.dtype), np.dtype(self.eltype)
+        if Ty.kind != "f" or Tx.kind not in "fiub":
+            raise TypeError("SparseInterpolator: source must be real, destination floating point")
+        T = np.dtype(np.float64) if np.float64 in (Ta.type, Tx.type) else np.dtype(np.float32)   # (integers promote to Ta)
+        table = self.table if T == Ta else self._promoted_table()
+        xs = np.asfortranarray(np.asarray(x), dtype=T)
+        tmp = np.empty(ar.shape_of(y), dtype=T, order="F")
+        run_tab(table, P is Adjoint, 1, 1, alpha, xs, 0, tmp, self.variant)
+        if float(beta) == 0.0:
+            y[...] = tmp.astype(Ty)
+        else:
+            y[...] = (tmp.astype(np.result_type(T, Ty)) + Ty.type(beta) * y).astype(Ty)
+        return y
+
     def _apply(self, alpha, P, x, scratch, beta, y):
-        x = ar.to_colmajor(x, self.eltype)
+        mixed = (not ar.is_device(x) and not ar.is_device(y) and isinstance(y, np.ndarray)
+                 and (np.asarray(x).dtype != self.eltype or y.dtype != self.eltype) and np.asarray(x).dtype.kind in "fiub")
+        x = np.asarray(x) if mixed else ar.to_colmajor(x, self.eltype)
         inp, out = (x, y) if P is Direct else (y, x)
         if len(ar.shape_of(inp)) != 1 or ar.shape_of(inp)[0] != self.ncols:
             raise _lib.ErrorException(f"bad vector length (expecting {self.ncols}, got {ar.shape_of(inp)})")   # :176-177
         if ar.shape_of(out) != self.dims:
             raise _lib.ErrorException(f"bad output array size (expecting {self.dims}, got {ar.shape_of(out)})")  # :178-179
+        if mixed and float(alpha) != 0.0:
+            return self._apply_mixed(alpha, P, x, beta, y)
+        if mixed:                       # alpha == 0: vscale!(y, beta) only (src/sparse.jl:211,255)
+            if float(beta) == 0.0:
+                y[...] = 0
+            else:
+                y *= y.dtype.type(beta)
+            return y
         check_dst(y, ar.shape_of(y), self.eltype)
         return run_tab(self.table, P is Adjoint, 1, 1, alpha, x, beta, y, self.variant)
 

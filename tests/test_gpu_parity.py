@@ -325,6 +325,37 @@ def test_gather_adjoint_is_deterministic(li):
         assert_close(got[0], O.tab_adjoint(J2, W2, 64, 1, y2, 0.5, 2, d0.copy(order="F")), TT)
 
 
+def test_sparse_interpolator_mixed_element_types(li):
+    """src/sparse.jl:201-275: x may be any Real, y any AbstractFloat; the sums run in float(promote_type(Ta, Tx))."""
+    rng = np.random.default_rng(12)
+    n, m = 300, 40
+    pos = rng.uniform(0.5, m + 0.5, n)
+    A = li.SparseInterpolator(li.CatmullRomSpline(np.float32), pos, m)
+    J, W = O.maketable(O.kernel(O.CATMULLROM, 4), pos.astype(np.float32), m, np.float32)
+    W64 = np.asfortranarray(W.astype(np.float64))
+    x64 = rng.standard_normal(m)                                 # Float64 data through a Float32 operator: Float64 sums
+    y64 = np.empty(n, dtype=np.float64)
+    li.apply_b(1, li.Direct, A, x64, False, 0, y64)
+    assert_close(y64, O.tab_direct(J, W64, m, 1, x64), np.float64)
+    y32 = rng.standard_normal(n).astype(np.float32)              # ... stored into a Float32 destination, beta != 0
+    want = (0.5 * np.asarray(O.tab_direct(J, W64, m, 1, x64)) + np.float32(2) * y32).astype(np.float32)
+    li.apply_b(0.5, li.Direct, A, x64, False, 2, y32)
+    np.testing.assert_allclose(y32, want, rtol=0, atol=2e-7 * np.max(np.abs(want)))
+    xi = rng.integers(-5, 6, m)                                  # integer data: promote_type(Float32, Int64) = Float32
+    yi = np.empty(n, dtype=np.float32)
+    li.apply_b(1, li.Direct, A, xi, False, 0, yi)
+    assert_close(yi, O.tab_direct(J, W, m, 1, xi.astype(np.float32)), np.float32)
+    z64 = np.empty(m, dtype=np.float64)                          # adjoint, Float64 source
+    li.apply_b(1, li.Adjoint, A, rng.standard_normal(n), False, 0, z64)
+    assert z64.dtype == np.float64 and np.isfinite(z64).all()
+    src = rng.standard_normal(n)
+    li.apply_b(1, li.Adjoint, A, src, False, 0, z64)
+    assert_close(z64, O.tab_adjoint(J, W64, m, 1, src), np.float64)
+    z0 = np.full(m, np.nan, dtype=np.float64)                    # alpha = 0, beta = 0: zero fill without reading
+    li.apply_b(0, li.Adjoint, A, src, False, 0, z0)
+    assert np.array_equal(z0, np.zeros(m))
+
+
 def test_imported_arbitrary_table(li):
     # user-defined tables (not window-shaped): generic gather path
     rng = np.random.default_rng(9)
