@@ -234,21 +234,15 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
         for (int j = 0; j < (D3 ? NBAR : NSTAGE - 1) && j < NJ; ++j) issue(j);
 
     // chunk metadata: rows per dst row (generic loop only), dim-2 weights
-    const int NV = vb - v0;                                   // dst rows v0 .. vb-1
     // (generic loop: for every src row of the chunk, the number of dst rows its folded window starts after the one of
     // the previous row -- dst rows that are complete before the row is added; bit 30 marks a window folded at an
     // edge of the array, where only the slots the clamped taps land on are fed)
-#ifdef ADS_OLD_GENERIC
-    if (!regular)
-        for (int k = tid; k < NRMAX; k += NT) sNv[k] = k < NV ? a.bp2[va + k + 1] - a.bp2[va + k] : 0;
-#else
     if (!regular)
         for (int k = tid; k < NR; k += NT) {
             const int b = a.base2[i2lo + k], bf = clampi(b, a.m2 - S2);
             const int prev = k == 0 ? v0 : clampi(a.base2[i2lo + k - 1], a.m2 - S2);
             sNv[k] = (bf - prev) | (b != bf ? (1 << 30) : 0);
         }
-#endif
     for (int k = tid; k < NR * S2; k += NT) sW2[k] = a.alpha * a.W2f[(int64_t)i2lo * S2 + k];
 
     // per-thread dim-1 taps: src columns [e0, e1) feed dst column c; staged window starts at a0 <= e0 (vector aligned)
@@ -425,66 +419,6 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
         }
     };
 
-#ifdef ADS_OLD_GENERIC
-    // ---- generic schedule: for dst row vv, every src row whose folded window starts at vv
-    auto run_generic = [&](auto clean, auto hasbeta) {
-        const T *pw = sW2;
-        const int *pn = sNv;
-        const T *prow = sS + off;
-        int left = 0;       // rows of the current stage not yet consumed
-        int j = -1;         // current stage
-        int k = 0;          // rows consumed (only the array-edge path needs it)
-        auto row = [&]() {
-            if (left == 0) {
-                prow = next_stage(++j);
-                left = K;
-            }
-            --left;
-            const T val = gather(prow, clean);
-            prow += rowstep;
-            return val;
-        };
-        for (int v = v0; v < vb; v += S2) {
-#pragma unroll
-            for (int u = 0; u < S2; ++u) {
-                const int vv = v + u;
-                if (vv < vb) {   // block-uniform
-                    int n = pn[u];
-                    if (vv > 0 && vv < a.m2 - S2) {   // interior windows: every slot is fed
-                        k += n;
-#pragma unroll 1
-                        for (; n > 0; --n) {
-                            const T val = row();
-                            T w2[S2];
-                            ld_weights<T, S2>(pw, w2);
-                            pw += S2;
-#pragma unroll
-                            for (int s = 0; s < S2; ++s) acc[(u + s) % S2] = fmaT(w2[s], val, acc[(u + s) % S2]);
-                        }
-                    } else {   // first / last window of the array: only the slots the clamped taps land on
-#pragma unroll 1
-                        for (; n > 0; --n) {
-                            const T val = row();
-                            T w2[S2];
-                            ld_weights<T, S2>(pw, w2);
-                            pw += S2;
-                            const int b = a.base2[i2lo + k];
-                            ++k;
-                            const int lo = clampi(b, a.m2 - 1) - vv, hi = clampi(b + S2 - 1, a.m2 - 1) - vv;
-#pragma unroll
-                            for (int s = 0; s < S2; ++s)
-                                if (s >= lo && s <= hi) acc[(u + s) % S2] = fmaT(w2[s], val, acc[(u + s) % S2]);
-                        }
-                    }
-                    emit(vv, acc[u], u, hasbeta);
-                    acc[u] = (T)0;
-                }
-            }
-            pn += S2;
-        }
-    };
-
-#else
     // ---- generic schedule: the src rows in order; acc[0] belongs to dst row `vcur`, and the window slides (register
     // moves) by as many dst rows as the folded window of the next src row starts later -- those rows are complete and
     // are stored.  Per dst row the contributions arrive in ascending src-row order, as in the reference's scatter.
@@ -556,7 +490,6 @@ sep2d_adj_stream_kernel(const SepArgs<T> a, const int CR, const int NRMAX)
         while (vcur < vb) advance();   // the last (at most S2) rows of the chunk
     };
 
-#endif
     // (every copy runs the same sequence of barriers, so warps of one CTA may take different copies)
     auto run = [&](auto hasbeta) {
         if (regular) {
@@ -710,11 +643,7 @@ static int stream_T(SepArgs<T> &a, const li_table *t1, const li_table *t2, int64
     rc = table_chunk_plan(t2, nchunks, 0.3, st, &a.cstart, &CR, &nrmax, &plan, taper.empty() ? nullptr : &taper, taper_key);
     if (rc != LI_OK) return rc;
     if (CR > 4096) return LI_OK;
-#ifdef ADS_OLD_GENERIC
-    const int NRMAX = (std::max(std::max(nrmax, 1), CR + 2 * S2) + 1) & ~1;
-#else
     const int NRMAX = (std::max(nrmax, 1) + 1) & ~1;
-#endif
     const size_t smem = (stage_elems * P1 + (size_t)NRMAX * S2) * sizeof(T) +
                         (size_t)NRMAX * sizeof(int) + NBAR * sizeof(uint64_t);
     if (trace)
