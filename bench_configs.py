@@ -70,6 +70,34 @@ def cfg1(li, torch):
             t = timeit(adj, 20)
             report(f"#1 sparse 1-D CatmullRom F64 {tag} adjoint {vname}", nrows, bytes_, t[0] - b0, t[1] - b0)
 
+            # the same calls replayed from a CUDA graph (100 launches back to back: no host in the loop, no L2 flush):
+            # config #1 is launch-latency bound, the graph shows the kernel itself
+            def graph_us(fn):
+                st, g = torch.cuda.Stream(), torch.cuda.CUDAGraph()
+                fn()
+                torch.cuda.synchronize()
+                with torch.cuda.stream(st):
+                    with torch.cuda.graph(g, stream=st):
+                        for _ in range(100):
+                            fn()
+                torch.cuda.synchronize()
+                g.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / 100
+            try:
+                if variant == li.VARIANT_GATHER:
+                    tg = graph_us(lambda: li.apply_b(1, li.Direct, A, x, False, 0, out))
+                    report(f"#1 {tag} forward, CUDA-graph replay (L2-resident)", nrows, bytes_, tg, tg)
+                tg = graph_us(lambda: li.apply_b(1, li.Adjoint, A, y, False, 0, back))
+                report(f"#1 {tag} adjoint {vname}, CUDA-graph replay (L2-resident)", nrows, bytes_, tg, tg)
+            except Exception as exc:   # pragma: no cover
+                print(json.dumps({"config": f"#1 {tag} graph replay", "error": f"{type(exc).__name__}: {exc}"}), flush=True)
+
 
 def cfg3(li, torch, nb):
     T = np.float32
