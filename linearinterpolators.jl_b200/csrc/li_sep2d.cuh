@@ -79,7 +79,8 @@ struct SepArgs {
     int tiles1, tiles2;
     int chunk0;                    // first chunk (along dim 2) of this launch: bands of the host-buffer pipeline
     int F1MAX, F2MAX;              // forward: footprint bounds; adjoint: F2MAX = max src rows feeding one row group
-    int vec_ok;                    // rows of the big array are 2-element-vector aligned
+    int vec_ok;                    // forward: bit 0 = source rows 16-byte aligned (TMA), bit 1 = destination rows vector
+                                   // aligned; tile adjoint: rows of the big array are 2-element-vector aligned
     T alpha, beta;
     const T *src;
     T *dst;

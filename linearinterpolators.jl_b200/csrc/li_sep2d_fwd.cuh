@@ -89,13 +89,13 @@ sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, c
 
     // footprint (tables are monotone): staged column c <-> source column lo1a + c, staged row r <-> lo2 + r
     const int lo1 = a.base1[i1_0], F1 = a.base1[min(i1_0 + TO1, a.n1) - 1] + S1 - lo1;
-    const int lo1a = a.vec_ok ? (lo1 & ~3) : lo1;
+    const int lo1a = (a.vec_ok & 1) ? (lo1 & ~3) : lo1;
     const int lo2 = a.base2[i2a];
     const int NR = a.base2[i2a + rows - 1] + S2 - lo2;        // source rows needed
     const int NJ = (NR + K - 1) / K;                         // stages
     // columns of the staged row that exist in the source; the rest are replicated edge columns
     const int cv0 = max(0, -lo1a), cv1 = min(P1, a.m1 - lo1a);
-    const bool bulk = a.vec_ok;                              // TMA bulk copies need 16-byte aligned row segments
+    const bool bulk = (a.vec_ok & 1) != 0;                   // TMA bulk copies need 16-byte aligned row segments
     const int need1 = min(P1, F1 + (lo1 - lo1a) + 1);        // staged columns actually read (incl. the spare tap)
     const bool patch = cv0 > 0 || cv1 < need1;
 
@@ -244,7 +244,7 @@ sep2d_fwd_kernel(const SepArgs<T> a, const int CR /* output rows per chunk */, c
     const int H1 = P1 >> 1;
     const int posA0 = (offA >> 1) + (offA & 1) * H1, posA1 = ((offA + 1) >> 1) + ((offA + 1) & 1) * H1;
     const int posB0 = (offB >> 1) + (offB & 1) * H1, posB1 = ((offB + 1) >> 1) + ((offB + 1) & 1) * H1;
-    const bool vec = a.vec_ok && haveB;
+    const bool vec = (a.vec_ok & 2) && haveB;
     const T *wp = sW2;                                  // weights of the next output row
     T *dp = dst + (int64_t)i2a * a.n1 + colA;           // next output element
     T hA[S2], hB[S2];
@@ -401,12 +401,14 @@ static int launch_fwd(SepArgs<T> &a, const li_table *t1, const li_table *t2, int
     a.F1MAX = (span1 + S1 + 1 + 3 + 3) & ~3;
     const int NCNT = (span2 + S2 + K - 1) / K * K;   // staged source rows of a chunk, padded to whole stages
     // 16-byte bulk copies need aligned source rows; 8-byte stores need aligned destination rows
-    a.vec_ok = (a.m1 % 4 == 0) && (((uintptr_t)a.src) % 16 == 0) && (a.n1 % 2 == 0) &&
-               (((uintptr_t)a.dst) % (2 * sizeof(T)) == 0);
+    // (bit 0: sources -- 16-byte bulk copies need aligned source rows; bit 1: destinations -- 8 / 16-byte stores need
+    // aligned destination rows)
+    a.vec_ok = (((a.m1 % 4 == 0) && (((uintptr_t)a.src) % 16 == 0)) ? 1 : 0) |
+               (((a.n1 % 2 == 0) && (((uintptr_t)a.dst) % (2 * sizeof(T)) == 0)) ? 2 : 0);
     const size_t smem = ((size_t)(NROWBUF + (D3 ? NBAR * a.nc3 : 0)) * K * a.F1MAX + (size_t)CR * S2) * sizeof(T) +
                         (size_t)((NCNT + 1) & ~1) * sizeof(int) + NBAR * sizeof(uint64_t);
     if (smem > (size_t)kSmemLimit) return LI_OK;   // footprint too large for staging: decline
-    if (D3 && !((a.m1 % 4 == 0) && (((uintptr_t)a.src) % 16 == 0))) return LI_OK;   // the raw ring is TMA only
+    if (D3 && !(a.vec_ok & 1)) return LI_OK;   // the raw ring is TMA only
     if (opt(OPT_TRACE))
         fprintf(stderr, "[li_b200] fwd%s: P1 %d CR %d K %d smem %zu tiles %d x %d x %lld\n", D3 ? " 3-D" : "", a.F1MAX, CR, K,
                 smem, a.tiles1, a.tiles2, (long long)nbatch);

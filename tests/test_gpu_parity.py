@@ -786,6 +786,9 @@ FUSED3D_CASES = [
     ("up3", (32, 12, 8), (32, 12, 25), (3, 3, 3), O.FLAT, (0.0, 0.0), True, False),
     # mixed sizes (S1, S2) = (2, 4) / S3 = 3
     ("mix", (24, 18, 10), (48, 18, 17), (1, 4, 2), O.FLAT, (0.4, 0.3), True, False),
+    # odd n1: destination rows are not vector aligned (scalar stores), the sources still arrive by TMA; the adjoint's
+    # source rows are unaligned -> per-dimension passes (found by scratch/fuzz_fused3d.py)
+    ("odd", (32, 49, 36), (185, 29, 12), (4, 8, 7), O.FLAT, (0.3, 0.6), True, False),
 ]
 
 
