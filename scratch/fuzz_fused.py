@@ -1,5 +1,5 @@
 """Randomised cross-check of the fused 2-D separable kernels against the per-dimension passes (both on the GPU).
-The fused path is toggled per call with LI_B200_NO_FUSED (read by the library at every apply)."""
+The fused path is toggled per call with li.set_option("no_fused", ...)."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,7 +7,8 @@ import li_b200 as li
 
 def kernels(T):
     return [li.LinearSpline(T), li.CatmullRomSpline(T), li.CubicSpline(T), li.LanczosKernel(T, 4), li.LanczosKernel(T, 6), li.QuadraticSpline(T),
-            li.SafeFlat(li.LanczosKernel(T, 4)), li.SafeFlat(li.CatmullRomSpline(T)), li.SafeFlat(li.LanczosKernel(T, 6))]
+            li.SafeFlat(li.LanczosKernel(T, 4)), li.SafeFlat(li.CatmullRomSpline(T)), li.SafeFlat(li.LanczosKernel(T, 6)),
+            li.LanczosKernel(T, 8), li.SafeFlat(li.LanczosKernel(T, 8)), li.SafeFlat(li.QuadraticSpline(T)), li.SafeFlat(li.LinearSpline(T))]
 
 def positions(style, m, n, rng):
     if style == 0: return np.linspace(1.0, float(m), n)
@@ -36,14 +37,13 @@ def main(ncases, seed):
         alpha, beta = (1.0, 0.0) if rng.random() < 0.5 else (float(rng.uniform(-2, 2)), float(rng.choice([0.0, 1.0, -0.5])))
         res = {}
         for mode in ("fused", "passes"):
-            if mode == "passes": os.environ["LI_B200_NO_FUSED"] = "1"
-            else: os.environ.pop("LI_B200_NO_FUSED", None)
+            li.set_option("no_fused", 1 if mode == "passes" else 0)
             out = li.to_device(np.asfortranarray(np.ones((n1, n2, nb), dtype=T)))
             back = li.to_device(np.asfortranarray(np.ones((m1, m2, nb), dtype=T)))
             li.sep_apply_tables(False, [A1.table, A2.table], alpha, src, beta, out, nbatch_dims=1)
             li.sep_apply_tables(True, [A1.table, A2.table], alpha, y, beta, back, nbatch_dims=1)
             res[mode] = (li.to_host(out).astype(np.float64), li.to_host(back).astype(np.float64))
-        os.environ.pop("LI_B200_NO_FUSED", None)
+        li.set_option("no_fused", 0)
         tol = (2e-5 if T == np.float32 else 1e-11)
         for idx, name in ((0, "forward"), (1, "adjoint")):
             a, b = res["fused"][idx], res["passes"][idx]
