@@ -85,6 +85,11 @@ function regularize!(A::DeviceArray{T,2}, eps::Real=RGL_EPS, mu::Real=RGL_MU) wh
 end
 regularize!(A::Matrix{T}, args...) where {T<:Floats} = copyto!(A, Array(regularize!(DeviceArray(A), args...)))
 regularize(A::AbstractMatrix{T}, args...) where {T<:Floats} = regularize!(copyto!(Array{T}(undef, size(A)), A), args...)
+function regularize(A::DeviceArray{T,2}, args...) where {T<:Floats}      # the regularized copy stays on the device
+    B = DeviceArray{T}(undef, size(A))
+    check(ccall((:li_memcpy_d2d, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), B.ptr, A.ptr, length(A) * sizeof(T), C_NULL))
+    return regularize!(B, args...)
+end
 
 SparseInterpolator(ker::Kernel{T}, args...) where {T<:AbstractFloat} = SparseInterpolator{T}(ker, args...)
 SparseInterpolator{T}(ker::Kernel, args...) where {T<:AbstractFloat} = SparseInterpolator{T}(T(ker), args...)
