@@ -81,6 +81,57 @@ def test_fused_kernels_match_oracle(seed):
     assert main(60, seed) == 0
 
 
+def main3d(ncases, seed):
+    """Three tables on dimensions 1-3: the fused 3-D kernels (or the passes they fall back to) against the oracle's three
+    passes in the reference's order (A3 first for Direct, A1' first for Adjoint)."""
+    global li
+    import li_b200 as li
+    from util import RO as O
+    rng = np.random.default_rng(seed)
+    worst = 0.0
+    for case in range(ncases):
+        T = np.float32 if rng.random() < 0.7 else np.float64
+        ks = kernels(T) + [li.SafeFlat(li.LinearSpline(T)), li.MitchellNetravaliSpline(T), li.LanczosKernel(T, 8)]
+        k = [ks[rng.integers(len(ks))] for _ in range(3)]
+        m = [int(rng.integers(6, 120)), int(rng.integers(6, 60)), int(rng.integers(4, 30))]
+        n = [int(rng.integers(4, 150)), int(rng.integers(4, 70)), int(rng.integers(3, 36))]
+        if rng.random() < 0.8: m[0] = (m[0] + 3) & ~3
+        if rng.random() < 0.7: n[0] = (n[0] + 3) & ~3
+        xs = [positions(int(rng.integers(4)), m[d], n[d], rng) for d in range(3)]
+        A = [li.TabulatedInterpolator(T, d + 1, k[d], xs[d], m[d]) for d in range(3)]
+        tabs = [a.table for a in A]
+        hs = np.asfortranarray(rng.standard_normal(m).astype(T))
+        hy = np.asfortranarray(rng.standard_normal(n).astype(T))
+        alpha, beta = (1.0, 0.0) if rng.random() < 0.5 else (float(rng.uniform(-2, 2)), float(rng.choice([0.0, 1.0, -0.5])))
+        d0 = np.asfortranarray(rng.standard_normal(n).astype(T))
+        c0 = np.asfortranarray(rng.standard_normal(m).astype(T))
+        out, back = li.to_device(d0), li.to_device(c0)
+        li.sep_apply_tables(False, tabs, alpha, li.to_device(hs), beta, out)
+        li.sep_apply_tables(True, tabs, alpha, li.to_device(hy), beta, back)
+        ref = O.tab_direct(A[2].J, A[2].W, m[2], 3, hs)
+        ref = O.tab_direct(A[1].J, A[1].W, m[1], 2, ref)
+        ref = O.tab_direct(A[0].J, A[0].W, m[0], 1, ref, alpha, beta, d0.copy(order="F"))
+        refa = O.tab_adjoint(A[0].J, A[0].W, m[0], 1, hy)
+        refa = O.tab_adjoint(A[1].J, A[1].W, m[1], 2, refa)
+        refa = O.tab_adjoint(A[2].J, A[2].W, m[2], 3, refa, alpha, beta, c0.copy(order="F"))
+        for got, want, name in ((li.to_host(out), ref, "forward"), (li.to_host(back), refa, "adjoint")):
+            err = _ratio(got, want, T)
+            worst = max(worst, err)
+            if not np.isfinite(err) or err > 1:
+                print(f"MISMATCH 3-D case {case} {name}: err / tol {err:.3e} T={np.dtype(T).name} "
+                      f"k={[type(q).__name__ + '/' + str(q.S) for q in k]} m={m} n={n} alpha={alpha} beta={beta}", flush=True)
+                return 1
+    print(f"{ncases} 3-D cases ok, worst err / tol = {worst:.3f}")
+    return 0
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_fused_3d_kernels_match_oracle(seed):
+    """Random kernels, sizes (odd first dimensions included), rates, clamped edges, alpha / beta, both element types: three
+    tables on dimensions 1-3 against the CPU oracle, per element at the stated tolerance."""
+    assert main3d(40, seed) == 0
+
+
 @pytest.mark.parametrize("seed", [21, 22])
 def test_affine_tiled_forward_is_bit_identical_to_per_pixel_kernel(seed):
     """Random affine transforms (rotation, anisotropic scale, shear, large offsets), sizes, kernels and batches: the
