@@ -25,7 +25,8 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 enum Option {
     OPT_NO_FUSED = 0,      // fused 2-D kernels off: per-dimension passes (cross-check of the fused kernels)
     OPT_NO_STREAM_DN,      // streaming / window kernels of li_tab_apply off: generic gather kernels
-    OPT_NO_BANDS,          // host-buffer pipeline off: upload, apply, download
+    OPT_NO_BANDS,          // 1: host-buffer pipeline off (upload, apply, download); 2..8: that many bands (default 8;
+                           // measured on config #2: 2 / 3 / 4 / 6 / 8 bands 7.9 / 7.75 / 7.6 / 8.1 / 7.8 ms per step, 16: 8.2)
     OPT_AFFINE_PLAIN,      // affine operators: one thread per pixel on global memory
     OPT_TRACE,             // print dispatch decisions to stderr
     OPT_ADJ_DEBUG,         // timing probes of the fused adjoint (see li_sep2d.cu)

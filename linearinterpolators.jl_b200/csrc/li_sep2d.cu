@@ -628,7 +628,7 @@ int sep2d_host_banded(int adjoint, const li_table *t1, const li_table *t2, doubl
 {
     *done = false;
     constexpr int NBMAX = 8;
-    if (opt(OPT_NO_BANDS) || !sep2d_fused_supported(t1, t2)) return LI_OK;
+    if (opt(OPT_NO_BANDS) == 1 || !sep2d_fused_supported(t1, t2)) return LI_OK;   // (values 2..8: that many bands)
     struct Guard {
         ~Guard() { sep2d_band() = nullptr; }
     } guard;
@@ -639,7 +639,7 @@ int sep2d_host_banded(int adjoint, const li_table *t1, const li_table *t2, doubl
     int rc = sep2d_fused_apply(adjoint, t1, t2, 1, alpha, dsrc, 0.0, ddst, st, &planned);
     if (rc != LI_OK || !planned) return rc;
     const int nchunks = (int)bc.src_end.size();
-    const int NB = std::min(NBMAX, nchunks);
+    const int NB = std::min(opt(OPT_NO_BANDS) >= 2 ? std::min(opt(OPT_NO_BANDS), NBMAX) : NBMAX, nchunks);
     if (NB < 2 || (int)bc.row_begin.size() != nchunks + 1) return LI_OK;
     const size_t es = t1->dtype == LI_F32 ? 4 : 8;
     const int64_t src_rows = adjoint ? t2->nrows : t2->ncols, src_w = adjoint ? t1->nrows : t1->ncols;
